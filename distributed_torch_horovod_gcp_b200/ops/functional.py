@@ -1,0 +1,107 @@
+"""Functional dispatch layer for the model zoo.
+
+Each function is ONE fusable unit.  ``*_reference`` are plain PyTorch compositions — the CPU
+path and the fp32 numerics oracle for the kernels' tests; the CUDA fast paths are the
+hand-written sm_100a kernels bound in ``ops.kernels`` (tcgen05 GEMM with fused epilogues,
+fused BN/ReLU/residual, LayerNorm, attention).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+_FORCE_REFERENCE = os.environ.get("B200DP_REFERENCE_OPS", "0") == "1"
+
+
+def _kernels(x: torch.Tensor):
+    """Return the kernels module when ``x`` can take the sm_100a path, else ``None``."""
+    if _FORCE_REFERENCE or not x.is_cuda:
+        return None
+    from . import kernels
+    return kernels if kernels.enabled_for(x) else None
+
+
+# ------------------------------------------------------------------ conv + BN (+ReLU, +residual)
+def conv_bn_act_reference(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool,
+                          residual: Optional[torch.Tensor] = None):
+    y = F.conv2d(x, conv.weight.to(x.dtype), None, conv.stride, conv.padding)
+    y = bn(y)
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y
+
+
+def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool = True,
+                residual: Optional[torch.Tensor] = None):
+    k = _kernels(x)
+    if k is not None and k.has("conv_bn_act"):
+        return k.conv_bn_act(x, conv, bn, relu, residual)
+    return conv_bn_act_reference(x, conv, bn, relu, residual)
+
+
+def max_pool_3x3_s2(x):
+    return F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+
+
+def global_avg_pool(x):
+    return x.mean(dim=(2, 3))
+
+
+# ------------------------------------------------------------------ linear (+bias, +act, +residual)
+def linear_reference(x, weight, bias=None, act: Optional[str] = None, residual=None):
+    y = F.linear(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype))
+    if act == "gelu":
+        y = F.gelu(y)
+    elif act == "relu":
+        y = F.relu(y)
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+def linear(x, weight, bias=None, act: Optional[str] = None, residual=None):
+    k = _kernels(x)
+    if k is not None and k.has("linear") and k.linear_supported(x, weight):
+        return k.linear(x, weight, bias, act, residual)
+    return linear_reference(x, weight, bias, act, residual)
+
+
+# ------------------------------------------------------------------ layer norm
+def layer_norm(x, weight, bias, eps: float = 1e-6):
+    k = _kernels(x)
+    if k is not None and k.has("layer_norm"):
+        return k.layer_norm(x, weight, bias, eps)
+    return F.layer_norm(x, (x.shape[-1],), weight.to(x.dtype), bias.to(x.dtype), eps)
+
+
+# ------------------------------------------------------------------ attention
+def attention_reference(qkv, heads: int):
+    B, S, D3 = qkv.shape
+    D = D3 // 3
+    hd = D // heads
+    q, k, v = qkv.view(B, S, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    o = F.scaled_dot_product_attention(q, k, v)
+    return o.transpose(1, 2).reshape(B, S, D)
+
+
+def attention(qkv, heads: int):
+    k = _kernels(qkv)
+    if k is not None and k.has("attention"):
+        return k.attention(qkv, heads)
+    return attention_reference(qkv, heads)
+
+
+# ------------------------------------------------------------------ ViT patch embedding
+def patch_embed(x, weight, bias, patch: int):
+    """``[B,3,H,W]`` (NCHW logical, any memory format) -> ``[B, (H/p)*(W/p), D]``: gather
+    non-overlapping patches to rows and run ONE GEMM against ``weight`` viewed as
+    ``[D, 3*p*p]`` (identical to the stride-p conv, but GEMM-shaped for tcgen05)."""
+    B, C, H, W = x.shape
+    gh, gw = H // patch, W // patch
+    cols = x.reshape(B, C, gh, patch, gw, patch).permute(0, 2, 4, 1, 3, 5) \
+            .reshape(B, gh * gw, C * patch * patch)
+    return linear(cols, weight.reshape(weight.shape[0], -1), bias)

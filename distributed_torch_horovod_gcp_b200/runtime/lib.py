@@ -1,0 +1,58 @@
+"""Locate / load the in-tree native libraries.
+
+  lib/libb200dp_rt.so       C++ runtime   (csrc/runtime.cpp)      — symmetric heap, fd passing
+  lib/libb200dp_comm.so     sm_100a comm  (csrc/comm_kernels.cu)  — allreduce/broadcast(+optimizer)
+  lib/libb200dp_kernels.so  sm_100a math  (csrc/gemm_sm100.cu …)  — tcgen05 GEMM, BN, LSTM …
+
+They are built IN-TREE by ``build.py`` (``__graft_entry__.build()``) so they travel with the
+repo snapshot to the GPU box, and loaded with ctypes (no torch headers => seconds to build).
+On a CUDA machine a missing library is an ERROR unless ``B200DP_ALLOW_FALLBACK=1``: tests
+must not silently pass on a PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(os.path.dirname(_HERE), "lib")
+_cache = {}
+
+
+def _path(name: str) -> str:
+    return os.path.join(LIB_DIR, name)
+
+
+def available(name: str = "libb200dp_comm.so") -> bool:
+    return os.path.exists(_path(name))
+
+
+def _load(name: str) -> Optional[ctypes.CDLL]:
+    if name in _cache:
+        return _cache[name]
+    p = _path(name)
+    lib = None
+    if os.path.exists(p):
+        lib = ctypes.CDLL(p, mode=ctypes.RTLD_GLOBAL)
+    else:
+        import torch
+        if torch.cuda.is_available() and os.environ.get("B200DP_ALLOW_FALLBACK", "0") != "1":
+            raise RuntimeError(
+                f"native library {p} is missing on a CUDA machine; run "
+                f"`python -c 'import __graft_entry__ as g; g.build()'` (or set "
+                f"B200DP_ALLOW_FALLBACK=1 to accept the PyTorch/NCCL fallback)")
+    _cache[name] = lib
+    return lib
+
+
+def load_runtime() -> Optional[ctypes.CDLL]:
+    return _load("libb200dp_rt.so")
+
+
+def load_comm() -> Optional[ctypes.CDLL]:
+    return _load("libb200dp_comm.so")
+
+
+def load_kernels() -> Optional[ctypes.CDLL]:
+    return _load("libb200dp_kernels.so")
