@@ -1,0 +1,239 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): images/sec for ResNet-50 synthetic-ImageNet bf16
+data-parallel training through ``hvd.DistributedOptimizer`` on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29511 bench.py --gpus 8 --steps 20 --warmup 5
+
+Prints ONE JSON line on rank 0.  ``value`` is whole-job images/s measured on the device
+(CUDA events, barrier + synchronize on both sides, max over ranks) for exactly ``--steps``
+full training steps (forward, backward, gradient allreduce, optimizer update).  ``e2e`` is
+the same metric through the public API with the per-step H2D copy of the inputs from pinned
+host memory and a D2H read of the loss inside the timed region.
+
+``--impl reference`` would run the unmodified reference from ``baseline/_ref``; the
+reference is a single script that needs the ``horovod`` and ``GPUtil`` packages and a
+network download — none are installable offline — so that arm prints
+``{"impl": "reference", "unavailable": ...}``.  ``--impl nccl_standin`` is the labelled
+NCCL stand-in baseline (DDP + cuDNN/cuBLAS + torch SGD), never reported as "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl_standin"])
+    p.add_argument("--model", default=os.environ.get("BENCH_MODEL", "resnet50"))
+    p.add_argument("--batch", type=int, default=int(os.environ.get("BENCH_BATCH", "256")),
+                   help="per-GPU batch (weak scaling)")
+    p.add_argument("--image-size", type=int, default=224)
+    p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--lr", type=float, default=0.1)
+    return p.parse_args()
+
+
+def reference_arm(args):
+    """Try to run the UNMODIFIED reference (baseline/_ref); report why it cannot run."""
+    why = None
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    script = os.path.join(ref_dir, "app", "torch_train.py")
+    try:
+        if not os.path.exists(script):
+            src = "/root/reference/app/torch_train.py"
+            if os.path.exists(src):
+                os.makedirs(os.path.dirname(script), exist_ok=True)
+                import shutil
+                shutil.copyfile(src, script)      # byte-identical copy, git-ignored
+        missing = []
+        for mod in ("horovod.torch", "GPUtil"):
+            try:
+                __import__(mod)
+            except Exception as e:  # noqa: BLE001
+                missing.append(f"{mod} ({type(e).__name__})")
+        if missing:
+            why = ("reference is one script (no setup.py/pyproject: pip install of /root/reference "
+                   "fails) that imports " + ", ".join(missing) + " — not installable offline "
+                   "(not in /opt/wheelhouse); it also downloads its dataset at import time")
+        elif not os.path.exists(script):
+            why = "baseline/_ref/app/torch_train.py missing and /root/reference not mounted"
+        else:
+            why = ("reference script has no benchmark mode for BASELINE.json's metric "
+                   "(ResNet-50 images/s); it only trains its LSTM on a downloaded CSV")
+    except Exception as e:  # noqa: BLE001
+        why = f"{type(e).__name__}: {e}"
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    if args.impl == "nccl_standin":
+        os.environ["B200DP_REFERENCE_OPS"] = "1"     # library cuDNN/cuBLAS ops only
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    import distributed_torch_horovod_gcp_b200.torch as hvd
+    from distributed_torch_horovod_gcp_b200.models import build
+    from distributed_torch_horovod_gcp_b200.data import SyntheticImageBatches
+    from distributed_torch_horovod_gcp_b200.utils.clocks import ClockSampler
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "bench.py needs a CUDA device", "n_gpus": 0}), flush=True)
+        return 1
+    hvd.init()
+    rank, world = hvd.rank(), hvd.size()
+    if world != args.gpus and rank == 0:
+        print(f"[bench] warning: --gpus {args.gpus} but world size is {world}", file=sys.stderr)
+    torch.cuda.set_device(hvd.local_rank())
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.backends.cudnn.benchmark = True
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+
+    torch.manual_seed(1234)
+    kw = {"num_classes": 1000}
+    if "vit" in args.model.lower():
+        kw["image_size"] = args.image_size
+    model = build(args.model, **kw).to(dev)
+    model = model.to(dtype).to(memory_format=torch.channels_last)
+    model.train()
+    base = torch.optim.SGD(model.parameters(), lr=args.lr, momentum=0.9, weight_decay=1e-4)
+
+    our_launches = lambda: 0
+    if args.impl == "ours":
+        os.environ.setdefault("B200DP_FUSED_SINGLE", "1")
+        opt = hvd.DistributedOptimizer(base, named_parameters=model.named_parameters())
+        hvd.broadcast_parameters(model.state_dict(), root_rank=0)
+        eng = opt.fused_engine
+        from distributed_torch_horovod_gcp_b200.ops import counters
+        our_launches = lambda: (eng.kernel_launches if eng is not None else 0) + counters.total()
+        step_model = model
+    else:
+        opt = base
+        if world > 1:
+            step_model = torch.nn.parallel.DistributedDataParallel(
+                model, device_ids=[dev.index], gradient_as_bucket_view=True)
+        else:
+            step_model = model
+
+    data = SyntheticImageBatches(args.batch, (3, args.image_size, args.image_size), 1000, dev,
+                                 dtype, ring=4, channels_last=True, seed=rank)
+    # device-resident batches for the device-timed region (inputs never re-created per step)
+    dev_batches = [data.next() for _ in range(2)]
+    torch.cuda.synchronize()
+
+    def train_step(x, y):
+        out = step_model(x)
+        loss = F.cross_entropy(out.float(), y)
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=(args.impl != "ours"))
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            hvd.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64)
+        return float(hvd.allreduce(t, op=hvd.Max))
+
+    # ---------------- warm-up (also cuDNN autotune / lazy allocations)
+    for i in range(max(args.warmup, 3)):
+        loss = train_step(*dev_batches[i % 2])
+    float(loss)
+    sync_all()
+
+    # ---------------- device-timed region: exactly --steps steps
+    sampler = ClockSampler(dev.index).start() if rank == 0 else None
+    l0 = our_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        loss = train_step(*dev_batches[i % 2])
+    e1.record()
+    sync_all()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = our_launches() - l0
+    final_loss = float(loss)
+
+    # ---------------- end-to-end region through the public API (H2D inputs + D2H loss per step)
+    e2e = None
+    if not args.no_e2e:
+        host_loss = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+        evs = []
+        for i in range(3):
+            train_step(*data.next())
+        sync_all()
+        e0.record()
+        for i in range(args.steps):
+            x, y = data.next()                       # H2D of this step's inputs (pinned -> device)
+            loss = train_step(x, y)
+            host_loss[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)   # D2H result
+            ev = torch.cuda.Event()
+            ev.record()
+            evs.append(ev)
+            if i >= 1:
+                evs[i - 1].synchronize()             # the training loop consumes the previous loss
+                _ = float(host_loss[i - 1])
+        e1.record()
+        sync_all()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e = {"value": round(args.batch * world * args.steps / (ms_e2e / 1e3), 2),
+               "unit": "images/sec", "ms_per_step": round(ms_e2e / args.steps, 3),
+               "h2d_bytes_per_step": int(data.bytes_per_batch), "d2h_bytes_per_step": 4}
+    clocks = sampler.stop() if sampler is not None else None
+
+    if rank == 0:
+        value = args.batch * world * args.steps / (ms / 1e3)
+        line = {
+            "metric": "images/sec (whole job, device-timed, max over ranks) ResNet-50 synthetic "
+                      "ImageNet training" if args.model == "resnet50" else
+                      f"images/sec (whole job, device-timed, max over ranks) {args.model} training",
+            "value": round(value, 2), "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic (random images/labels, random-init weights)",
+            "impl": args.impl,
+            "config": {"model": args.model, "global_batch": args.batch * world,
+                       "per_gpu_batch": args.batch, "image_size": args.image_size,
+                       "parallelism": f"dp{world}", "optimizer": "SGD momentum=0.9 wd=1e-4",
+                       "layout": "NHWC bf16",
+                       "l2": "no explicit flush: per-step working set (activations, several GB) "
+                             ">> 126 MB L2",
+                       "comm": (opt.fused_engine.algorithms() if args.impl == "ours" and
+                                getattr(opt, "fused_engine", None) is not None else
+                                ("nccl-ddp" if world > 1 else "none"))},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "final_loss": round(final_loss, 4),
+        }
+        print(json.dumps(line), flush=True)
+    hvd.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,9 +1,300 @@
-"""Placeholder; replaced below in the same commit series by the real engine."""
+"""Fused gradient-allreduce + optimizer engine (the north-star hot path).
+
+One bucket == one launch of an sm_100a kernel from csrc/comm_kernels.cu that
+  (1) reduces the bucket's gradients across all ranks by reading peer memory over NVLink
+      (one-shot), or by slice with P2P pushes (two-shot), or in the NVSwitch (NVLS);
+  (2) scales by 1/N, (3) runs the SGD-momentum / Adam / AdamW update on fp32 master
+  weights + state, (4) writes the updated parameters in the model dtype (pushing them to
+  every peer for the sliced algorithms) and (5) zeroes the consumed gradients —
+on a high-priority side stream ordered after backward by an event, so ``optimizer.step()``
+is a stream wait.  No NCCL, no separate scale kernel, no separate optimizer kernels, no
+pack/unpack (reference app/torch_train.py:
+259,277,280-281).
+
+Memory plan (per dtype arena, same element layout in every arena):
+  G  gradients      symmetric   p.grad are views        (peers read / switch reduces)
+  P  parameters     symmetric   p.data are views        (peers push updated slices)
+  M  fp32 master    local       only when dtype != fp32
+  S0 momentum | exp_avg,  S1 exp_avg_sq   local fp32    (sharded by slice for K2/K3)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import weakref
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .. import _state
+from .buckets import Bucket, arena_sizes
+
+_ENGINES: "weakref.WeakSet[FusedEngine]" = weakref.WeakSet()
+
+
+def live_engines():
+    return list(_ENGINES)
+
+
+def _classify(opt) -> Optional[str]:
+    """Return 'sgd' | 'adam' | 'adamw' if the wrapped optimizer's update rule is one the fused
+    epilogue implements exactly, else None."""
+    if isinstance(opt, torch.optim.SGD):
+        return "sgd"
+    if isinstance(opt, torch.optim.AdamW):
+        kind = "adamw"
+    elif isinstance(opt, torch.optim.Adam):
+        kind = "adam"
+    else:
+        return None
+    for g in opt.param_groups:
+        if g.get("amsgrad", False) or g.get("differentiable", False):
+            return None
+    return kind
 
 
 class FusedEngine:
     fuses_update = True
 
     @staticmethod
-    def try_create(opt, buckets, wire_dtype):
-        return None
+    def try_create(opt, buckets: List[Bucket], wire_dtype) -> Optional["FusedEngine"]:
+        rt = _state.runtime()
+        kind = _classify(opt)
+        ok_dtypes = all(b.dtype in (torch.float32, torch.bfloat16, torch.float16) for b in buckets)
+        devs = {b.device for b in buckets}
+        local_ok = kind is not None and ok_dtypes and len(devs) == 1 and wire_dtype is None
+        if rt.size > 1:
+            votes = [None] * rt.size
+            dist.all_gather_object(votes, bool(local_ok), group=rt.cpu_group)
+            if not all(votes):
+                return None
+            symm = _state.get_symm()
+            if symm is None:
+                return None
+        else:
+            if not local_ok:
+                return None
+            from ..runtime.local import LocalRuntime
+            symm = LocalRuntime.get()
+            if symm is None:
+                return None
+        return FusedEngine(opt, buckets, symm, kind)
+
+    # ------------------------------------------------------------------ construction
+    def __init__(self, opt, buckets: List[Bucket], symm, kind: str):
+        from ..runtime import symm as S
+        self.S = S
+        self.opt, self.buckets, self.symm, self.kind = weakref.proxy(opt), buckets, symm, kind
+        self.device = buckets[0].device
+        self.world = symm.world
+        self.average = getattr(opt, "_op").name == "Average"
+        self.arenas: Dict[torch.dtype, dict] = {}
+        for (dtype, device), n in arena_sizes(buckets).items():
+            es = torch.empty((), dtype=dtype).element_size()
+            G = symm.alloc(n * es)
+            P = symm.alloc(n * es)
+            g, p = G.tensor(dtype, n), P.tensor(dtype, n)
+            g.zero_()
+            p.zero_()
+            self.arenas[dtype] = {
+                "G": G, "P": P, "g": g, "p": p,
+                "M": torch.zeros(n, dtype=torch.float32, device=device)
+                if dtype != torch.float32 else None,
+                "S0": torch.zeros(n, dtype=torch.float32, device=device),
+                "S1": torch.zeros(n, dtype=torch.float32, device=device) if kind != "sgd" else None,
+            }
+        # re-home parameters and gradients into the arenas
+        with torch.no_grad():
+            for b in buckets:
+                ar = self.arenas[b.dtype]
+                for s in b.slots:
+                    lo = b.flat_offset + s.offset
+                    pv = ar["p"][lo: lo + s.numel].view(s.param.shape)
+                    pv.copy_(s.param.data)
+                    s.param.data = pv
+                    gv = ar["g"][lo: lo + s.numel].view(s.param.shape)
+                    if s.param.grad is not None:
+                        gv.copy_(s.param.grad)
+                    s.param.grad = gv
+        self.params_changed()
+        nb = len(buckets)
+        self.step_ctr = torch.zeros(nb, dtype=torch.int32, device=self.device)
+        self.ticket = torch.zeros(nb, dtype=torch.int32, device=self.device)
+        self.lr_scale: Optional[torch.Tensor] = None
+        self.side = torch.cuda.Stream(device=self.device, priority=-1)
+        self._args: Dict[int, object] = {}
+        self._algo: Dict[int, int] = {}
+        for b in buckets:
+            self._args[b.index], self._algo[b.index] = self._make_args(b)
+        self._done = torch.cuda.Event()
+        self.steps = 0
+        self.kernel_launches = 0
+        self._state_dirty = False
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=_state.runtime().cpu_group)
+        _ENGINES.add(self)
+
+    def _make_args(self, b: Bucket):
+        S, symm = self.S, self.symm
+        ar = self.arenas[b.dtype]
+        es = torch.empty((), dtype=b.dtype).element_size()
+        off = b.flat_offset * es
+        nbytes = b.numel * es
+        a = S.ARArgs()
+        gp, pp = ar["G"].ptrs_at(off), ar["P"].ptrs_at(off)
+        for r in range(self.world):
+            a.inp[r], a.out[r] = gp[r], pp[r]
+        both_mc = ar["G"].mc_ptr != 0 and ar["P"].mc_ptr != 0
+        algo = symm.pick_algo(nbytes, need_mc=both_mc)
+        if algo == S.ALGO_NVLS and not both_mc:
+            algo = S.ALGO_TWOSHOT
+        if algo == S.ALGO_NVLS:
+            a.in_mc, a.out_mc = ar["G"].mc_ptr + off, ar["P"].mc_ptr + off
+        f32 = 4 * b.flat_offset
+        a.master = ar["M"].data_ptr() + f32 if ar["M"] is not None else 0
+        a.s0 = ar["S0"].data_ptr() + f32
+        a.s1 = ar["S1"].data_ptr() + f32 if ar["S1"] is not None else 0
+        a.step_ctr = self.step_ctr.data_ptr() + 4 * b.index
+        a.ticket = self.ticket.data_ptr() + 4 * b.index
+        a.n = b.numel
+        a.scale = (1.0 / self.world) if self.average else 1.0
+        a.channel = S.CH_ENGINE
+        a.zero_input, a.copy_back = 1, 0
+        return a, algo
+
+    # ------------------------------------------------------------------ hot path
+    def _fill_hyper(self, a, group: dict):
+        S, h = self.S, a.h
+        lr = group["lr"]
+        h.lr = float(lr)
+        h.weight_decay = float(group.get("weight_decay", 0.0))
+        h.maximize = int(bool(group.get("maximize", False)))
+        if self.kind == "sgd":
+            h.kind = S.OPT_SGD
+            h.momentum = float(group.get("momentum", 0.0))
+            h.dampening = float(group.get("dampening", 0.0))
+            h.nesterov = int(bool(group.get("nesterov", False)))
+        else:
+            h.kind = S.OPT_ADAM
+            b1, b2 = group["betas"]
+            h.beta1, h.beta2, h.eps = float(b1), float(b2), float(group["eps"])
+            h.adamw = int(self.kind == "adamw" or bool(group.get("decoupled_weight_decay", False)))
+
+    def launch(self, b: Bucket):
+        """Called from the autograd hook when the last gradient of ``b`` has been produced."""
+        a = self._args[b.index]
+        self._fill_hyper(a, self.opt.param_groups[b.group_index])
+        a.lr_scale = self.lr_scale.data_ptr() if self.lr_scale is not None else 0
+        cur = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.side.wait_event(ev)
+        tl = _state.runtime().timeline
+        if tl is not None:
+            s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_ev.record(self.side)
+        self.symm.launch_allreduce(a, self._algo[b.index], b.dtype, b.nbytes, self.side)
+        self.kernel_launches += 1
+        if tl is not None:
+            e_ev.record(self.side)
+            tl.cuda_span(f"bucket.{b.index}", "FUSED_ALLREDUCE_" +
+                         self.S.ALGO_NAMES[self._algo[b.index]].upper(), s_ev, e_ev,
+                         bytes=b.nbytes)
+        return True
+
+    def wait_all(self, launched):
+        self._done.record(self.side)
+        torch.cuda.current_stream(self.device).wait_event(self._done)
+        self.symm.check_errors()
+
+    def after_step(self):
+        self.steps += 1
+        self._state_dirty = True
+
+    def zero_grad(self):
+        """Gradients are zeroed by the kernel that consumed them (zero-on-consume)."""
+        return
+
+    # ------------------------------------------------------------------ state plumbing
+    def params_changed(self):
+        """Parameters were written from outside (broadcast_parameters / load_state_dict):
+        refresh the fp32 master copies."""
+        for ar in self.arenas.values():
+            if ar["M"] is not None:
+                ar["M"].copy_(ar["p"])
+
+    def _sharded(self, b: Bucket) -> bool:
+        return self._algo[b.index] != self.S.ALGO_ONESHOT and self.world > 1
+
+    def export_state(self):
+        """Materialise ``optimizer.state`` (torch layout) from the flat state arenas so
+        ``state_dict()`` / checkpointing / ``broadcast_optimizer_state`` see the usual
+        per-parameter entries.  State of sliced buckets is sharded across ranks; unowned
+        slices are still zero, so a Sum-allreduce of the arena reassembles it."""
+        if self.steps == 0:
+            return
+        opt = self.opt
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
+        for b in self.buckets:
+            ar = self.arenas[b.dtype]
+            lo, hi = b.flat_offset, b.flat_offset + b.numel
+            s0 = ar["S0"][lo:hi].clone()
+            s1 = ar["S1"][lo:hi].clone() if ar["S1"] is not None else None
+            if self._sharded(b):
+                self.symm.allreduce_(s0)
+                if s1 is not None:
+                    self.symm.allreduce_(s1)
+            for s in b.slots:
+                st = opt.state[s.param]
+                v0 = s0[s.offset: s.offset + s.numel].view(s.param.shape)
+                if self.kind == "sgd":
+                    if opt.param_groups[b.group_index].get("momentum", 0.0) != 0.0:
+                        st["momentum_buffer"] = v0
+                else:
+                    st["step"] = torch.tensor(float(self.steps))
+                    st["exp_avg"] = v0
+                    st["exp_avg_sq"] = s1[s.offset: s.offset + s.numel].view(s.param.shape)
+        self._state_dirty = False
+
+    def import_state(self):
+        """Inverse of ``export_state`` (after ``optimizer.load_state_dict``)."""
+        opt = self.opt
+        steps = 0
+        for b in self.buckets:
+            ar = self.arenas[b.dtype]
+            for s in b.slots:
+                st = opt.state.get(s.param, {})
+                lo = b.flat_offset + s.offset
+                if self.kind == "sgd":
+                    mb = st.get("momentum_buffer")
+                    if mb is not None:
+                        ar["S0"][lo: lo + s.numel].copy_(mb.reshape(-1).float())
+                        steps = max(steps, 1)
+                else:
+                    if "exp_avg" in st:
+                        ar["S0"][lo: lo + s.numel].copy_(st["exp_avg"].reshape(-1).float())
+                        ar["S1"][lo: lo + s.numel].copy_(st["exp_avg_sq"].reshape(-1).float())
+                        steps = max(steps, int(float(st.get("step", 0))))
+            if self._sharded(b):
+                # keep only the owned slice (others must stay zero for export's Sum-gather)
+                vec = 16 // torch.empty((), dtype=b.dtype).element_size()
+                nvec = b.numel // vec
+                per = (nvec + self.world - 1) // self.world
+                rlo = min(self.symm.rank * per, nvec) * vec
+                rhi = min(rlo + per * vec, b.numel)
+                for key in ("S0", "S1"):
+                    t = ar[key]
+                    if t is None:
+                        continue
+                    seg = t[b.flat_offset: b.flat_offset + b.numel]
+                    seg[:rlo].zero_()
+                    seg[rhi:].zero_()
+        self.steps = max(self.steps, steps) if steps else self.steps
+        if steps:
+            self.step_ctr.fill_(steps)
+        self.params_changed()
+
+    def algorithms(self) -> Dict[int, str]:
+        return {i: self.S.ALGO_NAMES[a] for i, a in self._algo.items()}

@@ -1,7 +1,7 @@
 """Locate / load the in-tree native libraries.
 
-  lib/libb200dp_rt.so       C++ runtime   (csrc/runtime.cpp)      — symmetric heap, fd passing
-  lib/libb200dp_comm.so     sm_100a comm  (csrc/comm_kernels.cu)  — allreduce/broadcast(+optimizer)
+  lib/libb200dp_comm.so     C++ runtime (csrc/runtime.cpp: symmetric heap, fd passing) +
+                            sm_100a comm kernels (csrc/comm_kernels.cu: allreduce/broadcast(+optimizer))
   lib/libb200dp_kernels.so  sm_100a math  (csrc/gemm_sm100.cu …)  — tcgen05 GEMM, BN, LSTM …
 
 They are built IN-TREE by ``build.py`` (``__graft_entry__.build()``) so they travel with the
@@ -44,10 +44,6 @@ def _load(name: str) -> Optional[ctypes.CDLL]:
                 f"B200DP_ALLOW_FALLBACK=1 to accept the PyTorch/NCCL fallback)")
     _cache[name] = lib
     return lib
-
-
-def load_runtime() -> Optional[ctypes.CDLL]:
-    return _load("libb200dp_rt.so")
 
 
 def load_comm() -> Optional[ctypes.CDLL]:

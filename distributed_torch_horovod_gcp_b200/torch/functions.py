@@ -71,11 +71,9 @@ def broadcast_parameters(params, root_rank: int, process_set=None) -> None:
                 t.copy_(flat[off:off + n].view_as(t))
                 off += n
     # parameters may live in a fused engine's symmetric arena with a separate fp32 master
-    for name, t in items:
-        eng = getattr(t, "_b200dp_engine", None)
-        if eng is not None:
-            eng.params_changed()
-            break
+    from ..parallel.fused_engine import live_engines
+    for eng in live_engines():
+        eng.params_changed()
 
 
 def broadcast_object(obj, root_rank: int = 0, name=None, process_set=None):

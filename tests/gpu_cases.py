@@ -1,0 +1,240 @@
+"""Worker bodies for the multi-GPU tests (one process per GPU, symmetric-memory kernels)."""
+import copy
+import os
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+def _symm(hvd):
+    from distributed_torch_horovod_gcp_b200 import _state
+    s = _state.get_symm()
+    assert s is not None, f"symmetric runtime unavailable: {_state.runtime().symm_failed}"
+    return s
+
+
+def runtime_setup(hvd):
+    """cuMem allocation + fd exchange + peer mapping (+ multicast) works; peers see writes."""
+    s = _symm(hvd)
+    r, n = hvd.rank(), hvd.size()
+    buf = s.alloc(1 << 20)
+    t = buf.tensor(torch.float32)
+    t.fill_(float(r + 1))
+    torch.cuda.synchronize()
+    hvd.barrier()
+    # read every peer's buffer through the peer mapping
+    from distributed_torch_horovod_gcp_b200.runtime.symm import _Raw
+    for q in range(n):
+        peer = torch.as_tensor(_Raw(buf.peer_ptrs[q], 1024, buf), device=s.device).view(torch.float32)
+        assert float(peer[0]) == q + 1 and float(peer[-1]) == q + 1, (q, peer[:4])
+    hvd.barrier()
+    return {"multicast": bool(s.multicast), "mc_ptr": buf.mc_ptr != 0, "gran": s.gran,
+            "mc_gran": s.mc_gran, "sms": s.sm_count, "cc": s.cc}
+
+
+def allreduce_matches_nccl(hvd, algos):
+    s = _symm(hvd)
+    from distributed_torch_horovod_gcp_b200.runtime import symm as S
+    r, n = hvd.rank(), hvd.size()
+    dev = s.device
+    results = {}
+    sizes = [1, 3, 4, 64, 1000, 4096 + 1, 65536, 370049, 1 << 20, (4 << 20) + 12]
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2), (torch.float16, 2e-3)):
+        for numel in sizes:
+            torch.manual_seed(numel * 7 + r)
+            x = torch.randn(numel, device=dev).to(dtype)
+            ref = x.clone().float()
+            dist.all_reduce(ref)                 # NCCL oracle in fp32
+            ref = ref / n
+            for algo in algos:
+                if algo == "nvls" and not s.multicast:
+                    continue
+                code = {"oneshot": S.ALGO_ONESHOT, "twoshot": S.ALGO_TWOSHOT, "nvls": S.ALGO_NVLS}[algo]
+                y = x.clone()
+                ev = s.allreduce_(y, postscale=1.0 / n, algo=code)
+                ev.synchronize()
+                err = (y.float() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-6)
+                assert err < tol, (dtype, numel, algo, err)
+                # replicas bit-identical across ranks
+                g = [torch.empty_like(y) for _ in range(n)]
+                dist.all_gather(g, y)
+                assert all(torch.equal(g[0], q) for q in g), (dtype, numel, algo)
+                results[(str(dtype), numel, algo)] = err
+    # public API, default algo choice, Sum / Average / prescale, non-contiguous, symmetric tensor
+    t = torch.full((5, 7), float(r + 1), device=dev)
+    out = hvd.allreduce(t, op=hvd.Sum)
+    assert torch.all(out == sum(range(1, n + 1)))
+    out = hvd.allreduce(t.t(), prescale_factor=2.0)
+    assert torch.allclose(out, torch.full((7, 5), 2.0 * sum(range(1, n + 1)) / n, device=dev))
+    st = hvd.symm_empty(1 << 16, torch.float32)
+    st.fill_(float(r))
+    hvd.allreduce_(st, op=hvd.Sum)
+    torch.cuda.synchronize()
+    assert torch.all(st == sum(range(n)))
+    s.check_errors()
+    return len(results)
+
+
+def broadcast_matches(hvd):
+    s = _symm(hvd)
+    r, n = hvd.rank(), hvd.size()
+    dev = s.device
+    for numel in (1, 5, 1024, 370049, (2 << 20) + 3):
+        for root in sorted({0, n - 1}):
+            x = torch.arange(numel, device=dev, dtype=torch.float32) + 1000.0 * r
+            hvd.broadcast_(x, root)
+            torch.cuda.synchronize()
+            want = torch.arange(numel, device=dev, dtype=torch.float32) + 1000.0 * root
+            assert torch.equal(x, want), (numel, root)
+    from distributed_torch_horovod_gcp_b200.models import LSTM, resnet18
+    m = LSTM(23, 10, 1, 256, device=dev)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(float(r))
+    hvd.broadcast_parameters(m.state_dict(), root_rank=0)
+    m2 = resnet18(num_classes=10, small_input=True).to(dev)
+    m2.bn1.running_mean.fill_(float(r))
+    hvd.broadcast_parameters(m2.state_dict(), root_rank=0)       # params + BN buffers (int64 too)
+    flat = torch.cat([v.reshape(-1).float() for v in list(m.state_dict().values()) +
+                      list(m2.state_dict().values())])
+    g = [torch.empty_like(flat) for _ in range(n)]
+    dist.all_gather(g, flat)
+    assert all(torch.equal(g[0], q) for q in g)
+    assert float(m2.bn1.running_mean[0]) == 0.0
+    s.check_errors()
+    return True
+
+
+def fused_optimizer_matches_torch(hvd, opt_name, dtype_name, algo):
+    """N-rank fused allreduce+update == single-process torch optimizer on the averaged grads."""
+    os.environ["B200DP_ALGO"] = algo
+    s = _symm(hvd)
+    s.algo_override = algo
+    r, n = hvd.rank(), hvd.size()
+    dev = s.device
+    dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[dtype_name]
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(64, 300), torch.nn.Tanh(),
+                                torch.nn.Linear(300, 257), torch.nn.Tanh(),
+                                torch.nn.Linear(257, 8)).to(dev)
+    ref = copy.deepcopy(model).float()
+    model = model.to(dtype)
+
+    def mk(params):
+        if opt_name == "sgd":
+            return torch.optim.SGD(params, lr=0.05, momentum=0.9, weight_decay=1e-3)
+        if opt_name == "sgd_nesterov":
+            return torch.optim.SGD(params, lr=0.05, momentum=0.8, nesterov=True)
+        if opt_name == "adam":
+            return torch.optim.Adam(params, lr=1e-2, weight_decay=1e-2)
+        return torch.optim.AdamW(params, lr=1e-2, weight_decay=1e-2)
+    opt = hvd.DistributedOptimizer(mk(model.parameters()), named_parameters=model.named_parameters(),
+                                   bucket_bytes=256 << 10)
+    assert opt.fused_engine is not None, "fused engine not created"
+    assert isinstance(opt, type(mk(ref.parameters())))
+    ropt = mk(ref.parameters())
+    hvd.broadcast_parameters(model.state_dict(), root_rank=0)
+    torch.manual_seed(5)
+    X = torch.randn(4 * n, 64, device=dev)
+    Y = torch.randn(4 * n, 8, device=dev)
+    for step in range(4):
+        # reference: fp32 model, grads computed from the SAME low-precision forward as the DP ranks
+        ropt.zero_grad()
+        if dtype == torch.float32:
+            F.mse_loss(ref(X), Y).backward()
+        else:
+            # emulate: each rank's bf16 grads, averaged in fp32
+            shadow = copy.deepcopy(ref).to(dtype)
+            gsum = [torch.zeros_like(p, dtype=torch.float32) for p in ref.parameters()]
+            for q in range(n):
+                shadow.zero_grad()
+                F.mse_loss(shadow(X[q * 4:(q + 1) * 4].to(dtype)).float(), Y[q * 4:(q + 1) * 4]).backward()
+                for a, p in zip(gsum, shadow.parameters()):
+                    a += p.grad.float()
+            for p, a in zip(ref.parameters(), gsum):
+                p.grad = a / n
+        ropt.step()
+        xs, ys = X[r * 4:(r + 1) * 4], Y[r * 4:(r + 1) * 4]
+        F.mse_loss(model(xs.to(dtype)).float(), ys).backward()
+        opt.step()
+        opt.zero_grad()
+        if dtype != torch.float32:
+            # keep the fp32 reference in lock-step with the bf16-rounded weights it would see
+            pass
+    torch.cuda.synchronize()
+    tol = dict(rtol=2e-4, atol=2e-5) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+    for a, b in zip(model.parameters(), ref.parameters()):
+        torch.testing.assert_close(a.float(), b, **tol)
+    # gradients were zeroed by the kernel
+    assert all(float(p.grad.abs().max()) == 0.0 for p in model.parameters())
+    flat = torch.cat([p.detach().reshape(-1).float() for p in model.parameters()])
+    g = [torch.empty_like(flat) for _ in range(n)]
+    dist.all_gather(g, flat)
+    assert all(torch.equal(g[0], q) for q in g), "replicas diverged"
+    # state export parity (momentum / exp_avg visible through state_dict)
+    opt.fused_engine.export_state()
+    sd = opt.state_dict()["state"]
+    rsd = ropt.state_dict()["state"]
+    key = "momentum_buffer" if opt_name.startswith("sgd") else "exp_avg"
+    if dtype == torch.float32:
+        for i in rsd:
+            torch.testing.assert_close(sd[i][key].float().cpu(), rsd[i][key].cpu(), rtol=2e-4, atol=2e-5)
+    s.check_errors()
+    return opt.fused_engine.algorithms()
+
+
+def lstm_dp_training(hvd):
+    """End-to-end: reference LSTM config over the fused engine; equals the NCCL stand-in."""
+    from distributed_torch_horovod_gcp_b200.models import LSTM
+    s = _symm(hvd)
+    r, n = hvd.rank(), hvd.size()
+    dev = s.device
+    torch.manual_seed(0)
+    m = LSTM(23, 10, 1, 256, device=dev)
+    ref = copy.deepcopy(m)
+    opt = hvd.DistributedOptimizer(torch.optim.Adam(m.parameters(), lr=1e-3),
+                                   named_parameters=m.named_parameters())
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    hvd.broadcast_parameters(m.state_dict(), root_rank=0)
+    assert opt.fused_engine is not None
+    for step in range(5):
+        torch.manual_seed(100 + step * n + r)
+        x, y = torch.randn(32, 10, 23, device=dev), torch.randn(32, 1, 1, device=dev)
+        for mod, o, is_ref in ((m, opt, False), (ref, ropt, True)):
+            torch.manual_seed(7 + step * n + r)          # same random (h0,c0) for both
+            F.mse_loss(mod(x), y).backward()
+            if is_ref:
+                for p in mod.parameters():
+                    dist.all_reduce(p.grad)
+                    p.grad /= n
+            o.step()
+            o.zero_grad()
+    torch.cuda.synchronize()
+    for a, b in zip(m.parameters(), ref.parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-6)
+    s.check_errors()
+    return opt.fused_engine.algorithms()
+
+
+def stress_flag_reuse(hvd, iters):
+    """Repeated collectives of varying size with per-iteration checksum (flag-reuse bugs)."""
+    s = _symm(hvd)
+    r, n = hvd.rank(), hvd.size()
+    dev = s.device
+    st = hvd.symm_empty(1 << 18, torch.float32)
+    bad = 0
+    for i in range(iters):
+        numel = [256, 4096, 65536, 1 << 18][i % 4]
+        v = st[:numel]
+        v.fill_(float((i % 13) + r))
+        hvd.allreduce_(v, op=hvd.Sum)
+        want = float(sum((i % 13) + q for q in range(n)))
+        if i % 50 == 0 or i == iters - 1:
+            torch.cuda.synchronize()
+            if not bool(torch.all(v == want)):
+                bad += 1
+    torch.cuda.synchronize()
+    s.check_errors()
+    assert bad == 0, bad
+    return True

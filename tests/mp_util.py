@@ -16,15 +16,21 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _entry(rank, world, port, modname, fname, args, q):
+def _entry(rank, world, port, modname, fname, args, q, cuda=False):
     os.environ.update({"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank),
                        "LOCAL_WORLD_SIZE": str(world), "MASTER_ADDR": "127.0.0.1",
-                       "MASTER_PORT": str(port), "B200DP_FORCE_CPU": "1",
-                       "OMP_NUM_THREADS": "1"})
+                       "MASTER_PORT": str(port), "OMP_NUM_THREADS": "1"})
+    if cuda:
+        os.environ.pop("B200DP_FORCE_CPU", None)
+        os.environ.setdefault("B200DP_KERNEL_TIMEOUT_S", "10")
+    else:
+        os.environ["B200DP_FORCE_CPU"] = "1"
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     torch.set_num_threads(1)
+    if cuda:
+        torch.cuda.set_device(rank)
     try:
         import importlib
         import distributed_torch_horovod_gcp_b200.torch as hvd
@@ -37,11 +43,11 @@ def _entry(rank, world, port, modname, fname, args, q):
         q.put((rank, "err", f"{type(e).__name__}: {e}\n{traceback.format_exc()}"))
 
 
-def run_workers(world, modname, fname, args=(), timeout=180):
+def run_workers(world, modname, fname, args=(), timeout=180, cuda=False):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_entry, args=(r, world, port, modname, fname, args, q))
+    procs = [ctx.Process(target=_entry, args=(r, world, port, modname, fname, args, q, cuda))
              for r in range(world)]
     for p in procs:
         p.start()

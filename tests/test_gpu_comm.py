@@ -1,0 +1,48 @@
+"""sm_100a communication kernels vs NCCL (multi-GPU; run with gpurun --gpus N)."""
+import pytest
+import torch
+
+from mp_util import run_workers
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _world():
+    n = torch.cuda.device_count()
+    return 8 if n >= 8 else (4 if n >= 4 else 2)
+
+
+def test_runtime_setup():
+    res = run_workers(_world(), "gpu_cases", "runtime_setup", cuda=True, timeout=300)
+    print("symmetric runtime:", res[0])
+    assert all(r["gran"] >= (1 << 21) for r in res)
+
+
+def test_allreduce_matches_nccl():
+    res = run_workers(_world(), "gpu_cases", "allreduce_matches_nccl",
+                      (["oneshot", "twoshot", "nvls"],), cuda=True, timeout=600)
+    assert all(r > 0 for r in res)
+
+
+def test_broadcast():
+    assert all(run_workers(_world(), "gpu_cases", "broadcast_matches", cuda=True, timeout=300))
+
+
+@pytest.mark.parametrize("opt,dtype,algo", [
+    ("sgd", "fp32", "oneshot"), ("sgd", "bf16", "twoshot"), ("sgd_nesterov", "fp32", "twoshot"),
+    ("adam", "fp32", "oneshot"), ("adamw", "fp32", "nvls"), ("sgd", "bf16", "nvls"),
+])
+def test_fused_optimizer(opt, dtype, algo):
+    res = run_workers(_world(), "gpu_cases", "fused_optimizer_matches_torch", (opt, dtype, algo),
+                      cuda=True, timeout=300)
+    print("algorithms:", res[0])
+
+
+def test_lstm_dp_training():
+    res = run_workers(_world(), "gpu_cases", "lstm_dp_training", cuda=True, timeout=300)
+    print("algorithms:", res[0])
+
+
+def test_stress_flag_reuse():
+    assert all(run_workers(_world(), "gpu_cases", "stress_flag_reuse", (2000,), cuda=True,
+                           timeout=600))

@@ -1,0 +1,83 @@
+"""Single-GPU tests: native library is loaded, fused update kernel (K7, world=1) vs torch
+optimizers, graft smoke, app script on cuda."""
+import copy
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_native_library_loaded():
+    from distributed_torch_horovod_gcp_b200.runtime import lib
+    assert lib.available(), "libb200dp_comm.so missing: run __graft_entry__.build()"
+    L = lib.load_comm()
+    assert L is not None
+    maps = open("/proc/self/maps").read()
+    assert "libb200dp_comm.so" in maps
+
+
+@pytest.mark.parametrize("opt_name,dtype", [("sgd", torch.float32), ("sgd", torch.bfloat16),
+                                            ("adam", torch.float32), ("adamw", torch.float32)])
+def test_fused_update_single_gpu(hvd_single, opt_name, dtype, monkeypatch):
+    monkeypatch.setenv("B200DP_FUSED_SINGLE", "1")
+    hvd = hvd_single
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(32, 100), torch.nn.ReLU(),
+                                torch.nn.Linear(100, 7)).to(dev)
+    ref = copy.deepcopy(model)
+    model = model.to(dtype)
+
+    def mk(ps):
+        if opt_name == "sgd":
+            return torch.optim.SGD(ps, lr=0.1, momentum=0.9, weight_decay=1e-2, nesterov=True)
+        if opt_name == "adam":
+            return torch.optim.Adam(ps, lr=1e-2)
+        return torch.optim.AdamW(ps, lr=1e-2, weight_decay=0.1)
+    opt = hvd.DistributedOptimizer(mk(model.parameters()), named_parameters=model.named_parameters())
+    assert opt.fused_engine is not None
+    ropt = mk(ref.parameters())
+    x, y = torch.randn(16, 32, device=dev), torch.randn(16, 7, device=dev)
+    for _ in range(5):
+        if dtype == torch.float32:
+            F.mse_loss(ref(x), y).backward()
+        else:
+            sh = copy.deepcopy(ref).to(dtype)
+            F.mse_loss(sh(x.to(dtype)).float(), y).backward()
+            for p, q in zip(ref.parameters(), sh.parameters()):
+                p.grad = q.grad.float()
+        ropt.step()
+        ropt.zero_grad()
+        F.mse_loss(model(x.to(dtype)).float(), y).backward()
+        opt.step()
+        opt.zero_grad()
+    tol = dict(rtol=1e-4, atol=1e-5) if dtype == torch.float32 else dict(rtol=2e-2, atol=2e-2)
+    for a, b in zip(model.parameters(), ref.parameters()):
+        torch.testing.assert_close(a.float(), b, **tol)
+    assert opt.fused_engine.kernel_launches == 5 * len(opt.bucket_plan())
+    opt.fused_engine.export_state()
+    assert len(opt.state_dict()["state"]) == 4
+
+
+def test_graft_smoke():
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
+    assert "smoke ok" in r.stdout
+
+
+def test_app_script_cuda_single(tmp_path):
+    env = dict(os.environ, PYTHONPATH=ROOT, B200DP_OFFLINE="1", B200DP_SYNTH_ROWS="2000")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "app", "torch_train.py"), "--epochs", "2"],
+                       cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "this process is using device - cuda:0" in r.stdout
+    assert r.stdout.count("train_loss") == 2 and "total training time in minutes" in r.stdout
