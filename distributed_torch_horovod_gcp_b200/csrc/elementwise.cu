@@ -1,0 +1,328 @@
+// Fused NHWC bf16 batch-norm kernels for sm_100a (memory-bound; 128-bit vector access).
+//
+// A channels-last activation is a row-major [M = N*H*W, C] matrix, so per-channel statistics are
+// column reductions and normalisation is a per-column affine.  Fusions (vs the eager
+// BN -> add -> ReLU chain, SURVEY.md §7.1 step 9 "fused BN+ReLU"):
+//   forward : stats pass (1 read) + ONE apply pass  y = relu(x*a[c] + b[c] + residual)
+//             (3 reads + 1 write instead of 5 reads + 3 writes)
+//   backward: reduce pass with the ReLU mask recomputed from y, + ONE apply pass that writes dx and
+//             the residual-branch gradient together.
+// Statistics accumulate in fp32 (vector registers -> shared -> one atomicAdd per block/channel).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace {
+
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& x, float* f) {
+  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    f[2 * t] = __uint_as_float(w[t] << 16);
+    f[2 * t + 1] = __uint_as_float(w[t] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint32_t w[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+    w[t] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// Column reduction scaffold: the flattened vector index i (8 channels per vector) maps to channel
+// group i % V.  The total thread count is a multiple of V, so a thread always owns ONE channel
+// group and accumulates NACC x 8 partial sums in registers; threads of a block that share a group
+// are combined through shared memory and the block issues one atomicAdd per (channel, quantity).
+template <int NACC>
+__device__ __forceinline__ void block_reduce_to_global(float (&acc)[NACC][8], int V, float* const* outs) {
+  __shared__ float sm[THREADS][8 + 1];
+  const int tid = threadIdx.x;
+  const int groups = THREADS / V;      // threads per channel group inside this block (>=1)
+#pragma unroll
+  for (int q = 0; q < NACC; ++q) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[tid][j] = acc[q][j];
+    __syncthreads();
+    if (tid < V) {
+      float s[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = 0.f;
+      for (int g = 0; g < groups; ++g) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += sm[tid + g * V][j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(outs[q] + tid * 8 + j, s[j]);
+    }
+  }
+}
+
+// ---- forward statistics: sum[c], sumsq[c] -------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) bn_stats_kernel(const uint4* __restrict__ x, float* sum,
+                                                           float* sumsq, long long nvec, int V) {
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  const long long stride = (long long)gridDim.x * THREADS;
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < nvec; i += stride) {
+    float f[8];
+    unpack8(ldg_stream(x + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += f[j];
+      acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
+    }
+  }
+  float* outs[2] = {sum, sumsq};
+  block_reduce_to_global<2>(acc, V, outs);
+}
+
+// ---- finalize: mean/invstd, affine (a, b), running statistics ------------------------------------
+__device__ __forceinline__ float ld_param(const void* p, int c, int bf16) {
+  return bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[c])
+              : reinterpret_cast<const float*>(p)[c];
+}
+__device__ __forceinline__ void st_param(void* p, int c, int bf16, float v) {
+  if (bf16) reinterpret_cast<__nv_bfloat16*>(p)[c] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(p)[c] = v;
+}
+
+// gamma/beta/running_* are the module's tensors in their own dtype (fp32 or bf16: `pbf16`).
+__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const void* gamma,
+                                   const void* beta, float* mean, float* invstd, float* a, float* b,
+                                   void* running_mean, void* running_var, float count, float eps,
+                                   float momentum, int C, int pbf16) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float m = sum[c] / count;
+  const float var = fmaxf(sumsq[c] / count - m * m, 0.f);
+  const float is = rsqrtf(var + eps);
+  mean[c] = m;
+  invstd[c] = is;
+  const float g = gamma ? ld_param(gamma, c, pbf16) : 1.f;
+  a[c] = g * is;
+  b[c] = (beta ? ld_param(beta, c, pbf16) : 0.f) - m * g * is;
+  if (running_mean) {
+    const float unbiased = var * (count / fmaxf(count - 1.f, 1.f));
+    st_param(running_mean, c, pbf16, (1.f - momentum) * ld_param(running_mean, c, pbf16) + momentum * m);
+    st_param(running_var, c, pbf16,
+             (1.f - momentum) * ld_param(running_var, c, pbf16) + momentum * unbiased);
+  }
+}
+
+// ---- forward apply: y = relu(x*a + b + residual) ---------------------------------------------------
+__global__ void __launch_bounds__(THREADS) bn_apply_kernel(const uint4* __restrict__ x,
+                                                           const uint4* __restrict__ res, uint4* y,
+                                                           const float* __restrict__ a,
+                                                           const float* __restrict__ b, long long nvec,
+                                                           int V, int relu) {
+  const long long stride = (long long)gridDim.x * THREADS;
+  const long long i0 = (long long)blockIdx.x * THREADS + threadIdx.x;
+  if (i0 >= nvec) return;
+  const int cg = (int)(i0 % V);
+  float av[8], bv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    av[j] = a[cg * 8 + j];
+    bv[j] = b[cg * 8 + j];
+  }
+  for (long long i = i0; i < nvec; i += stride) {
+    float f[8];
+    unpack8(ldg_stream(x + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], av[j], bv[j]);
+    if (res) {
+      float r[8];
+      unpack8(ldg_stream(res + i), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    y[i] = pack8(f);
+  }
+}
+
+// ---- backward reduce: sum_dy[c], sum_dy_xhat[c] (dy masked by y > 0 when relu) ----------------------
+__global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(
+    const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y,
+    const float* __restrict__ mean, const float* __restrict__ invstd, float* sum_dy, float* sum_dy_xhat,
+    long long nvec, int V, int relu) {
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  const long long stride = (long long)gridDim.x * THREADS;
+  const long long i0 = (long long)blockIdx.x * THREADS + threadIdx.x;
+  float mv[8], iv[8];
+  {
+    const int cg = (int)(i0 % V);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mv[j] = mean[cg * 8 + j];
+      iv[j] = invstd[cg * 8 + j];
+    }
+  }
+  for (long long i = i0; i < nvec; i += stride) {
+    float g[8], xv[8];
+    unpack8(ldg_stream(dy + i), g);
+    unpack8(ldg_stream(x + i), xv);
+    if (relu) {
+      float yv[8];
+      unpack8(ldg_stream(y + i), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += g[j];
+      acc[1][j] = fmaf(g[j], (xv[j] - mv[j]) * iv[j], acc[1][j]);
+    }
+  }
+  float* outs[2] = {sum_dy, sum_dy_xhat};
+  block_reduce_to_global<2>(acc, V, outs);
+}
+
+// ---- backward apply: dx = a*(dz - sum_dy/M - xhat*sum_dy_xhat/M), dres = dz ------------------------
+__global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(
+    const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y, uint4* dx,
+    uint4* dres, const float* __restrict__ mean, const float* __restrict__ invstd,
+    const float* __restrict__ scale_a, const float* __restrict__ sum_dy,
+    const float* __restrict__ sum_dy_xhat, float inv_count, long long nvec, int V, int relu) {
+  const long long stride = (long long)gridDim.x * THREADS;
+  const long long i0 = (long long)blockIdx.x * THREADS + threadIdx.x;
+  if (i0 >= nvec) return;
+  const int cg = (int)(i0 % V);
+  float mv[8], iv[8], k1[8], k2[8], sc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cg * 8 + j;
+    mv[j] = mean[c];
+    iv[j] = invstd[c];
+    sc[j] = scale_a[c];      // gamma * invstd, saved by the forward
+    k1[j] = sum_dy[c] * inv_count;
+    k2[j] = sum_dy_xhat[c] * inv_count;
+  }
+  for (long long i = i0; i < nvec; i += stride) {
+    float g[8], xv[8], o[8];
+    unpack8(ldg_stream(dy + i), g);
+    unpack8(ldg_stream(x + i), xv);
+    if (relu) {
+      float yv[8];
+      unpack8(ldg_stream(y + i), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xhat = (xv[j] - mv[j]) * iv[j];
+      o[j] = sc[j] * (g[j] - k1[j] - xhat * k2[j]);
+    }
+    dx[i] = pack8(o);
+    if (dres) dres[i] = pack8(g);
+  }
+}
+
+thread_local char g_err[256];
+int fail(const char* what, cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return -1;
+}
+
+int grid_for(long long nvec, int V) {
+  long long blocks = (nvec + THREADS * 4 - 1) / (THREADS * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  // total threads must be a multiple of V (V is a power of two <= 256 => always true)
+  return (int)blocks;
+}
+
+bool shape_ok(int C) {
+  const int V = C / 8;
+  return C % 8 == 0 && V >= 1 && V <= THREADS && (THREADS % V) == 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200dp_ew_last_error() { return g_err; }
+
+int b200dp_bn_supported(int C) { return shape_ok(C) ? 1 : 0; }
+
+// stats: [2*C] fp32, zeroed by this call.  Writes mean/invstd/a/b ([C] fp32 each); updates running stats.
+int b200dp_bn_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta,
+                  float* stats, float* mean, float* invstd, float* a, float* b, void* running_mean,
+                  void* running_var, long long M, int C, float eps, float momentum, int relu,
+                  int param_bf16, unsigned long long stream) {
+  if (!shape_ok(C)) {
+    snprintf(g_err, sizeof(g_err), "unsupported channel count %d", C);
+    return -1;
+  }
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  const int V = C / 8;
+  const long long nvec = M * V;
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C, st);
+  if (e != cudaSuccess) return fail("memset", e);
+  const int grid = grid_for(nvec, V);
+  bn_stats_kernel<<<grid, THREADS, 0, st>>>((const uint4*)x, stats, stats + C, nvec, V);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, stats + C, gamma, beta, mean, invstd, a, b,
+                                                      running_mean, running_var, (float)M, eps, momentum, C,
+                                                      param_bf16);
+  bn_apply_kernel<<<grid, THREADS, 0, st>>>((const uint4*)x, (const uint4*)res, (uint4*)y, a, b, nvec, V,
+                                            relu);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("bn_fwd launch", e);
+  return 0;
+}
+
+// Inference / frozen-statistics apply: y = relu(x*a + b + res) with caller-provided a, b.
+int b200dp_bn_apply(const void* x, const void* res, void* y, const float* a, const float* b, long long M,
+                    int C, int relu, unsigned long long stream) {
+  if (!shape_ok(C)) return -1;
+  const int V = C / 8;
+  const long long nvec = M * V;
+  bn_apply_kernel<<<grid_for(nvec, V), THREADS, 0, (cudaStream_t)(uintptr_t)stream>>>(
+      (const uint4*)x, (const uint4*)res, (uint4*)y, a, b, nvec, V, relu);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("bn_apply launch", e);
+  return 0;
+}
+
+// sums: [2*C] fp32 (zeroed here): sum_dy | sum_dy_xhat  (== dbeta | dgamma).
+int b200dp_bn_bwd(const void* dy, const void* x, const void* y, void* dx, void* dres, const float* scale_a,
+                  const float* mean, const float* invstd, float* sums, long long M, int C, int relu,
+                  unsigned long long stream) {
+  if (!shape_ok(C)) return -1;
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  const int V = C / 8;
+  const long long nvec = M * V;
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
+  if (e != cudaSuccess) return fail("memset", e);
+  const int grid = grid_for(nvec, V);
+  bn_bwd_reduce_kernel<<<grid, THREADS, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint4*)y, mean,
+                                                 invstd, sums, sums + C, nvec, V, relu);
+  bn_bwd_apply_kernel<<<grid, THREADS, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint4*)y,
+                                                (uint4*)dx, (uint4*)dres, mean, invstd, scale_a, sums,
+                                                sums + C, 1.0f / (float)M, nvec, V, relu);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("bn_bwd launch", e);
+  return 0;
+}
+
+}  // extern "C"

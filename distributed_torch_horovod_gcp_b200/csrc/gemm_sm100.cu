@@ -1,0 +1,540 @@
+// bf16 GEMM for sm_100a: TMA -> shared (128B swizzle) -> tcgen05.mma -> TMEM -> fused epilogue.
+//
+//   C[M,N] (+)= act( A[M,K] * B[N,K]^T + bias[N] ) + residual[M,N]
+//
+// A and B can each be K-major (row-major [rows][K]) or MN-major (stored [K][rows]), so the
+// same kernel serves linear / 1x1-conv forward (A=x, B=W), dgrad (A=dy, B=W as MN-major) and
+// wgrad (A=dy^T, B=x^T, both MN-major, split-K with fp32 atomics) without any transpose pass.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma, UMMA 128xBNx16,
+//                 accumulator in TMEM, tcgen05.commit releases smem stages / publishes the tile)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b.x32 -> registers -> bias/act/residual -> global)
+//   smem ring of kStages {A 128x64, B BNx64} tiles; TMEM double-buffered accumulators so the
+//   epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// This replaces the cuBLAS addmm / cuDNN 1x1-conv calls on the model zoo's hot path
+// (SURVEY.md §2.2 N13, §2.6 S5/S7, §7.1 step 9).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = 128 bytes = one 128B swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;     // 6 warps
+
+struct GemmParams {
+  int M, N, K;
+  int ldc;                 // elements
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int splits;              // split-K factor (>=1)
+  int act;                 // 0 none, 1 relu, 2 gelu(erf), 3 *gelu'(aux), 4 *(aux>0)  [aux = residual ptr]
+  int out_mode;            // 0: bf16 store, 1: fp32 atomic add (split-K / accumulate), 2: fp32 store
+  void* C;
+  const void* bias;        // bf16 [N] or nullptr
+  const void* bias_f32;    // fp32 [N] or nullptr
+  const void* residual;    // bf16 [M, ldc] or nullptr (added after act; or `aux` for act 3/4)
+  void* preact;            // optional bf16 [M, ldc]: pre-activation values (saved for backward)
+  float alpha;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait suspends for a bounded time per attempt; the attempt counter turns a protocol bug
+  // (lost arrive / wrong phase) into a trap ("unspecified launch failure") instead of a GPU hang.
+  uint32_t done = 0;
+  for (uint32_t tries = 0; !done; ++tries) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && tries > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 64-bit UMMA shared-memory descriptor (sm_100: version=1), 128B swizzle.
+//   K-major  : rows of 128 B (64 bf16 of K), 8-row groups 1024 B apart (SBO); LBO unused (=1).
+//   MN-major : [k rows][64 mn elements] atoms of 128 B rows; 8-row k-groups SBO=1024 B apart,
+//              64-element mn chunks LBO bytes apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                              uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+  return d;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // D format: F32
+  d |= 1u << 7;                      // A format: BF16
+  d |= 1u << 10;                     // B format: BF16
+  d |= (A_MN ? 1u : 0u) << 15;       // A major
+  d |= (B_MN ? 1u : 0u) << 16;       // B major
+  d |= (uint32_t)(BN >> 3) << 17;    // N
+  d |= (uint32_t)(BLOCK_M >> 4) << 24;  // M
+  return d;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& x, float* f) {
+  const uint32_t wv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    f[2 * t] = __uint_as_float(wv[t] << 16);
+    f[2 * t + 1] = __uint_as_float(wv[t] & 0xffff0000u);
+  }
+}
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint32_t wv[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+    wv[t] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(wv[0], wv[1], wv[2], wv[3]);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN;       // double-buffered fp32 accumulator
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;        // [STAGES]
+  uint64_t* tmem_full = bars + 2 * C::STAGES;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_base_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int work_items = tiles * p.splits;
+  const int kb_per_split = (p.num_k_blocks + p.splits - 1) / p.splits;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+        const int tile = w % tiles, split = w / tiles;
+        const int m_idx = (tile % p.num_m_blocks) * BLOCK_M;
+        const int n_idx = (tile / p.num_m_blocks) * BN;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, p.num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* sa = smem_a + stage * C::A_BYTES;
+          uint8_t* sb = smem_b + stage * C::B_BYTES;
+          const int k_idx = kb * BLOCK_K;
+          if (!A_MN) {
+            tma_load_2d(&map_a, &full_bar[stage], sa, k_idx, m_idx);           // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)                                // box {64 m, 64 k}
+              tma_load_2d(&map_a, &full_bar[stage], sa + c * (BLOCK_K * 128), m_idx + 64 * c, k_idx);
+          }
+          if (!B_MN) {
+            tma_load_2d(&map_b, &full_bar[stage], sb, k_idx, n_idx);           // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(&map_b, &full_bar[stage], sb + c * (BLOCK_K * 128), n_idx + 64 * c, k_idx);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+      const int split = w / tiles;
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb0 + kb_per_split, p.num_k_blocks);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
+          const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                     : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                     : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
+            tc_mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
+          if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[acc]);   // empty split: publish zeros path
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ============================ epilogue warps ============================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+      const int tile = w % tiles, split = w / tiles;
+      const int m_idx = (tile % p.num_m_blocks) * BLOCK_M;
+      const int n_idx = (tile / p.num_m_blocks) * BN;
+      const int kb0 = split * kb_per_split;
+      const bool has_k = min(kb0 + kb_per_split, p.num_k_blocks) > kb0;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_idx + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+        tc_ld_32x32b_x32(taddr, r);
+        tc_wait_ld();
+        const int col0 = n_idx + c0;
+        if (!row_ok || col0 >= p.N || !has_k) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+        const int ncols = min(32, p.N - col0);     // N % 8 == 0 is enforced by the host
+        if (p.out_mode == 0 || p.out_mode == 2) {
+          if (p.bias != nullptr) {
+            const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncols) v[i] += __bfloat162float(b[i]);
+          } else if (p.bias_f32 != nullptr) {
+            const float* b = reinterpret_cast<const float*>(p.bias_f32) + col0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncols) v[i] += b[i];
+          }
+          if (p.preact != nullptr) {
+            uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.preact) +
+                                                 (size_t)row * p.ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j * 8 < ncols) pp[j] = pack8(v + j * 8);
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+          }
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(
+                reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j * 8 < ncols) {
+                float a[8];
+                unpack8(rp[j], a);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  if (p.act == 3) v[j * 8 + t] *= gelu_erf_grad(a[t]);
+                  else if (p.act == 4) v[j * 8 + t] = a[t] > 0.0f ? v[j * 8 + t] : 0.0f;
+                  else v[j * 8 + t] += a[t];
+                }
+              }
+            }
+          }
+        }
+        if (p.out_mode == 0) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) +
+                                                (size_t)row * p.ldc + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j * 8 < ncols) dst[j] = pack8(v + j * 8);
+        } else {
+          float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+          if (p.out_mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j * 4 < ncols)
+                reinterpret_cast<float4*>(dst)[j] =
+                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncols) atomicAdd(dst + i, v[i]);     // RED.ADD.F32 (split-K accumulation)
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+thread_local char g_err[512];
+int g_num_sms = 0;
+
+int fail(const char* msg, int code = 0) {
+  snprintf(g_err, sizeof(g_err), "%s (%d)", msg, code);
+  return -1;
+}
+
+int ensure_init() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult st;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &st);
+  if (e != cudaSuccess || st != cudaDriverEntryPointSuccess || !fn)
+    return fail("cuTensorMapEncodeTiled entry point unavailable", (int)e);
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  return 0;
+}
+
+// 2D bf16 tensor map: `rows` x `cols` (cols contiguous), row pitch `ld` elements, box {64, box_rows}.
+int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed", (int)r);
+  return 0;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int max_ctas, cudaStream_t st) {
+  using C = Cfg<BN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);
+    attr_set = true;
+  }
+  const int work = p.num_m_blocks * p.num_n_blocks * p.splits;
+  int grid = work < g_num_sms ? work : g_num_sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200dp_gemm_last_error() { return g_err; }
+
+// A: K-major -> [M][lda>=K]; MN-major -> [K][lda>=M].   B: K-major -> [N][ldb>=K]; MN-major -> [K][ldb>=N].
+// C: [M][ldc>=N].  out_mode 0: bf16 = act(alpha*AB + bias) + residual; 1: fp32 atomic +=; 2: fp32 store.
+// Requirements: K % 8 == 0 for K-major operands, M % 8 (A) / N % 8 (B) == 0 for MN-major, N % 8 == 0,
+// 16-byte aligned base pointers and leading dimensions.
+int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                     int a_mn, int b_mn, const void* bias_bf16, const void* bias_f32, const void* residual,
+                     void* preact, int act, int out_mode, float alpha, int splits, int block_n, int max_ctas,
+                     unsigned long long stream) {
+  if (ensure_init()) return -1;
+  if (M <= 0 || N <= 0 || K <= 0) return fail("bad shape");
+  if ((N % 8) || (lda % 8) || (ldb % 8) || (ldc % 4) || ((out_mode == 0) && (ldc % 8)))
+    return fail("alignment: N, lda, ldb, ldc must be multiples of 8");
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) return fail("pointers must be 16-byte aligned");
+  int BN = block_n;
+  if (BN == 0) BN = (N > 128) ? 256 : (N > 64 ? 128 : 64);
+  if (BN != 64 && BN != 128 && BN != 256) return fail("block_n must be 64/128/256");
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc;
+  p.num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_blocks = (N + BN - 1) / BN;
+  p.num_k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  p.splits = splits < 1 ? 1 : splits;
+  if (p.splits > p.num_k_blocks) p.splits = p.num_k_blocks;
+  if (p.splits > 1 && out_mode != 1) return fail("split-K requires out_mode=1 (fp32 atomic add)");
+  {  // no empty splits
+    const int per = (p.num_k_blocks + p.splits - 1) / p.splits;
+    p.splits = (p.num_k_blocks + per - 1) / per;
+  }
+  p.act = act; p.out_mode = out_mode; p.C = C; p.bias = bias_bf16; p.bias_f32 = bias_f32;
+  p.residual = residual; p.preact = preact; p.alpha = alpha;
+  CUtensorMap ma, mb;
+  if (a_mn ? make_map(&ma, A, K, M, lda, BLOCK_K) : make_map(&ma, A, M, K, lda, BLOCK_M)) return -1;
+  if (b_mn ? make_map(&mb, B, K, N, ldb, BLOCK_K) : make_map(&mb, B, N, K, ldb, BN)) return -1;
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+#define DISPATCH(BNV)                                                                         \
+  if (BN == BNV) {                                                                            \
+    if (!a_mn && !b_mn) return launch<BNV, false, false>(ma, mb, p, max_ctas, st);            \
+    if (!a_mn && b_mn) return launch<BNV, false, true>(ma, mb, p, max_ctas, st);              \
+    if (a_mn && !b_mn) return launch<BNV, true, false>(ma, mb, p, max_ctas, st);              \
+    return launch<BNV, true, true>(ma, mb, p, max_ctas, st);                                  \
+  }
+  DISPATCH(64)
+  DISPATCH(128)
+  DISPATCH(256)
+#undef DISPATCH
+  return fail("unreachable");
+}
+
+}  // extern "C"

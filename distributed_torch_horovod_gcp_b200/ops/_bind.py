@@ -1,11 +1,19 @@
-"""ctypes signatures + autograd wrappers for the compute kernels.  Filled in as kernels land;
-``register`` marks an op available only if its C symbol exists in the built library."""
+"""ctypes signatures + autograd wrappers for the compute kernels.  ``register`` marks an op
+available only if its C symbol exists in the built library."""
 from __future__ import annotations
 
-import ctypes
 from typing import Dict
+
+from . import gemm as _gemm
+from . import bn as _bn
+from .gemm import linear  # noqa: F401  (re-exported as kernels.linear)
+from .bn import conv_bn_act, bn_act  # noqa: F401
 
 
 def register(lib, have: Dict[str, bool]) -> None:
-    from . import gemm as _gemm
     _gemm.register(lib, have)
+    _bn.register(lib, have)
+
+
+def linear_supported(x, weight) -> bool:
+    return _gemm.supported(x, weight)

@@ -1,0 +1,141 @@
+"""Fused NHWC BatchNorm(+residual)(+ReLU) (csrc/elementwise.cu) and the conv+BN+act unit used by
+the ResNet blocks.  1x1 stride-1 convolutions run on the tcgen05 GEMM (an NHWC activation is a
+row-major [N*H*W, C] matrix); other convolutions use cuDNN until the implicit-GEMM kernel lands."""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import counters
+from . import gemm as _gemm
+
+_lib = None
+_USE_GEMM_1X1 = os.environ.get("B200DP_CONV1X1_GEMM", "1") == "1"
+
+
+def register(lib, have):
+    global _lib
+    if not hasattr(lib, "b200dp_bn_fwd"):
+        return
+    _lib = lib
+    vp, i, f, ll, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_uint64
+    lib.b200dp_bn_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, i, i, u64]
+    lib.b200dp_bn_apply.argtypes = [vp, vp, vp, vp, vp, ll, i, i, u64]
+    lib.b200dp_bn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, i, u64]
+    lib.b200dp_bn_supported.argtypes = [i]
+    lib.b200dp_ew_last_error.restype = ctypes.c_char_p
+    have["bn_act"] = True
+    have["conv_bn_act"] = True
+
+
+def _ck(rc):
+    if rc != 0:
+        raise RuntimeError("elementwise kernel: " + (_lib.b200dp_ew_last_error() or b"").decode())
+
+
+def _nhwc_ok(x: torch.Tensor) -> bool:
+    return x.dim() == 4 and x.dtype == torch.bfloat16 and \
+        x.is_contiguous(memory_format=torch.channels_last) and x.data_ptr() % 16 == 0
+
+
+def bn_supported(x: torch.Tensor, C: int) -> bool:
+    return _lib is not None and _nhwc_ok(x) and bool(_lib.b200dp_bn_supported(C))
+
+
+class _BNActFn(torch.autograd.Function):
+    """Training-mode BN over NHWC bf16 with fused residual add and ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, relu, eps, momentum):
+        N, C, H, W = x.shape
+        M = N * H * W
+        dev = x.device
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        ws = torch.empty(6 * C, dtype=torch.float32, device=dev)
+        stats, mean, invstd, a, b = ws[:2 * C], ws[2 * C:3 * C], ws[3 * C:4 * C], ws[4 * C:5 * C], ws[5 * C:]
+        pbf16 = int(gamma.dtype == torch.bfloat16)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _ck(_lib.b200dp_bn_fwd(x.data_ptr(), residual.data_ptr() if residual is not None else None,
+                               y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
+                               mean.data_ptr(), invstd.data_ptr(), a.data_ptr(), b.data_ptr(),
+                               running_mean.data_ptr() if running_mean is not None else None,
+                               running_var.data_ptr() if running_var is not None else None,
+                               M, C, float(eps), float(momentum), int(relu), pbf16, st))
+        counters.bump("bn_fwd", 3)
+        ctx.save_for_backward(x, y if relu else None, mean, invstd, a)
+        ctx.relu, ctx.has_res, ctx.pdtype = relu, residual is not None, gamma.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, invstd, a = ctx.saved_tensors
+        N, C, H, W = x.shape
+        M = N * H * W
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        dres = torch.empty_like(x, memory_format=torch.channels_last) if (ctx.has_res and ctx.relu) \
+            else None
+        sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _ck(_lib.b200dp_bn_bwd(dy.data_ptr(), x.data_ptr(), y.data_ptr() if y is not None else None,
+                               dx.data_ptr(), dres.data_ptr() if dres is not None else None,
+                               a.data_ptr(), mean.data_ptr(), invstd.data_ptr(), sums.data_ptr(),
+                               M, C, int(ctx.relu), st))
+        counters.bump("bn_bwd", 2)
+        dbeta = sums[:C].to(ctx.pdtype)
+        dgamma = sums[C:].to(ctx.pdtype)
+        if ctx.has_res and dres is None:
+            dres = dy                       # no ReLU: the residual branch gets dy unchanged
+        return dx, dgamma, dbeta, None, None, dres, None, None, None
+
+
+def bn_act(x, bn: torch.nn.BatchNorm2d, relu: bool, residual: Optional[torch.Tensor] = None):
+    if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
+        residual = residual.contiguous(memory_format=torch.channels_last)
+    if bn.training:
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        return _BNActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
+                              relu, bn.eps, mom)
+    # inference: frozen statistics -> one fused apply pass
+    a = (bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps))
+    b = bn.bias.float() - bn.running_mean.float() * a
+    y = torch.empty_like(x, memory_format=torch.channels_last)
+    N, C, H, W = x.shape
+    _ck(_lib.b200dp_bn_apply(x.data_ptr(), residual.data_ptr() if residual is not None else None,
+                             y.data_ptr(), a.data_ptr(), b.data_ptr(), N * H * W, C, int(relu),
+                             torch.cuda.current_stream(x.device).cuda_stream))
+    counters.bump("bn_apply")
+    return y
+
+
+def conv2d(x, conv: torch.nn.Conv2d):
+    """Convolution of an NHWC bf16 activation; 1x1/stride-1 -> tcgen05 GEMM."""
+    w = conv.weight
+    if (_USE_GEMM_1X1 and _gemm._lib is not None and conv.kernel_size == (1, 1)
+            and conv.stride == (1, 1) and conv.padding == (0, 0) and conv.groups == 1
+            and conv.bias is None and w.dtype == torch.bfloat16 and _nhwc_ok(x)
+            and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0):
+        N, C, H, W = x.shape
+        x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, C)             # view: NHWC rows
+        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C))              # [M, Cout]
+        return y2.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2)      # logical NCHW, NHWC memory
+    return F.conv2d(x, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+
+def conv_bn_act(x, conv, bn, relu: bool, residual=None):
+    y = conv2d(x, conv)
+    C = y.shape[1]
+    if bn_supported(y, C) and bn.weight is not None and \
+            (residual is None or residual.dtype == torch.bfloat16):
+        return bn_act(y, bn, relu, residual)
+    y = bn(y)
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y
