@@ -136,23 +136,36 @@ def test_fused_bn_matches_torch(C, relu, res):
 
 
 def test_resnet50_kernels_vs_reference_ops():
-    """Whole-model check: the kernel path (tcgen05 1x1 convs + fused BN) vs the library path."""
-    import os
+    """Whole-model check: the kernel path (tcgen05 1x1 convs + fused BN) must be as close to an
+    fp32 run of the same model as the library bf16 path is (bf16 noise through 53 BN layers is
+    large, so the two bf16 paths are each compared with the fp32 oracle, not with each other)."""
+    import copy
     from distributed_torch_horovod_gcp_b200.models import resnet50
     from distributed_torch_horovod_gcp_b200.ops import functional as F2
     torch.manual_seed(5)
-    m = resnet50(num_classes=64).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
-    x = torch.randn(8, 3, 64, 64, device="cuda").to(torch.bfloat16).contiguous(
-        memory_format=torch.channels_last)
-    y = m(x)
-    y.float().sum().backward()
-    g1 = m.fc.weight.grad.clone()
-    m.zero_grad()
+    m32 = resnet50(num_classes=64).cuda().to(memory_format=torch.channels_last)
+    m = copy.deepcopy(m32).to(torch.bfloat16)
+    x32 = torch.randn(32, 3, 64, 64, device="cuda").contiguous(memory_format=torch.channels_last)
+    x = x32.to(torch.bfloat16)
     F2._FORCE_REFERENCE = True
     try:
+        y32 = m32(x32)
+        y32.sum().backward()
         yr = m(x)
         yr.float().sum().backward()
+        gr = m.fc.weight.grad.clone()
+        cr = m.layer1[0].conv1.weight.grad.clone()
     finally:
         F2._FORCE_REFERENCE = False
-    assert _rel(y, yr) < 5e-2
-    assert _rel(g1, m.fc.weight.grad) < 1e-1
+    m.zero_grad()
+    y = m(x)
+    y.float().sum().backward()
+    e_ref, e_ker = _rel(yr, y32), _rel(y, y32)
+    print("fwd rel err vs fp32: library", e_ref, "kernels", e_ker)
+    assert e_ker < max(2.0 * e_ref, 0.05)
+    g_ref, g_ker = _rel(gr, m32.fc.weight.grad), _rel(m.fc.weight.grad, m32.fc.weight.grad)
+    c_ref, c_ker = _rel(cr, m32.layer1[0].conv1.weight.grad), \
+        _rel(m.layer1[0].conv1.weight.grad, m32.layer1[0].conv1.weight.grad)
+    print("grad rel err vs fp32: fc", g_ref, g_ker, "layer1.0.conv1", c_ref, c_ker)
+    assert g_ker < max(2.0 * g_ref, 0.05)
+    assert c_ker < max(2.5 * c_ref, 0.1)
