@@ -81,15 +81,16 @@ def main():
                 nv = nccl_buf[:n]
                 ms = timed(lambda: dist.all_reduce(nv), iters, warm)
             elif a == "auto":
-                ms = timed(lambda: symm.allreduce_(view, postscale=1.0 / world), iters, warm)
-                row["auto_algo"] = S.ALGO_NAMES[symm.pick_algo(nbytes, need_mc=buf.mc_ptr != 0)]
+                fn = symm.prepare_allreduce(view, 1.0 / world)
+                ms = timed(fn, iters, warm)
+                row["auto_algo"] = fn.algo
             else:
                 if a == "nvls" and not (symm.multicast and buf.mc_ptr):
                     continue
                 if a == "oneshot" and nbytes > (64 << 20):
                     continue                      # (N-1)x traffic: pointless and slow at these sizes
-                c = code[a]
-                ms = timed(lambda: symm.allreduce_(view, postscale=1.0 / world, algo=c), iters, warm)
+                fn = symm.prepare_allreduce(view, 1.0 / world, algo=code[a])
+                ms = timed(fn, iters, warm)
             row[a + "_us"] = round(ms * 1e3, 2)
             row[a + "_busGBs"] = round(2 * (world - 1) / world * nbytes / (ms * 1e-3) / 1e9, 2)
             full.fill_(1.0)

@@ -441,37 +441,58 @@ __global__ void __launch_bounds__(512) allreduce_sliced_kernel(CommCtx c, ARArgs
   const StepInfo s = make_step(a);
 
   rank_barrier(c, a.channel);
-  for (size_t v = lo + start; v < hi; v += stride) {
-    float acc[VN];
+  // U independent 16-byte transactions per thread are issued before any is consumed: NVLink
+  // round trips are ~2 us, so bytes-in-flight (not instruction count) bounds the bandwidth.
+  constexpr int U = kNVLS ? 4 : 2;
+  for (size_t v0 = lo + start; v0 < hi; v0 += U * stride) {
+    float acc[U][VN];
     if (kNVLS) {
-      const uint4 red = Vec<T>::mc_reduce(reinterpret_cast<const uint4*>(a.in_mc) + v);
-      Vec<T>::unpack(red, acc);
+      uint4 red[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t v = v0 + u * stride;
+        if (v < hi) red[u] = Vec<T>::mc_reduce(reinterpret_cast<const uint4*>(a.in_mc) + v);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) Vec<T>::unpack(red[u], acc[u]);
     } else {
-      uint4 raw[B200DP_MAX_RANKS];
+      uint4 raw[U][B200DP_MAX_RANKS];
 #pragma unroll
-      for (int r = 0; r < B200DP_MAX_RANKS; ++r)
-        if (r < c.world) raw[r] = ld_peer_v4(reinterpret_cast<const uint4*>(a.in[r]) + v);
-      float f[VN];
+      for (int u = 0; u < U; ++u) {
+        const size_t v = v0 + u * stride;
 #pragma unroll
-      for (int i = 0; i < VN; ++i) acc[i] = 0.0f;
+        for (int r = 0; r < B200DP_MAX_RANKS; ++r)
+          if (r < c.world && v < hi) raw[u][r] = ld_peer_v4(reinterpret_cast<const uint4*>(a.in[r]) + v);
+      }
 #pragma unroll
-      for (int r = 0; r < B200DP_MAX_RANKS; ++r) {
-        if (r < c.world) {
-          Vec<T>::unpack(raw[r], f);
+      for (int u = 0; u < U; ++u) {
+        float f[VN];
 #pragma unroll
-          for (int i = 0; i < VN; ++i) acc[i] += f[i];
+        for (int i = 0; i < VN; ++i) acc[u][i] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < B200DP_MAX_RANKS; ++r) {
+          if (r < c.world) {
+            Vec<T>::unpack(raw[u][r], f);
+#pragma unroll
+            for (int i = 0; i < VN; ++i) acc[u][i] += f[i];
+          }
         }
       }
     }
-    float o[VN];
-    epilogue<T, VN>(a, s, v * VN, acc, reinterpret_cast<const T*>(a.out[c.rank]), o);
-    const uint4 packed = Vec<T>::pack(o);
-    if (kNVLS) {
-      mc_st_v4(reinterpret_cast<uint4*>(a.out_mc) + v, packed);
-    } else {
 #pragma unroll
-      for (int r = 0; r < B200DP_MAX_RANKS; ++r)
-        if (r < c.world) st_peer_v4(reinterpret_cast<uint4*>(a.out[r]) + v, packed);
+    for (int u = 0; u < U; ++u) {
+      const size_t v = v0 + u * stride;
+      if (v >= hi) break;
+      float o[VN];
+      epilogue<T, VN>(a, s, v * VN, acc[u], reinterpret_cast<const T*>(a.out[c.rank]), o);
+      const uint4 packed = Vec<T>::pack(o);
+      if (kNVLS) {
+        mc_st_v4(reinterpret_cast<uint4*>(a.out_mc) + v, packed);
+      } else {
+#pragma unroll
+        for (int r = 0; r < B200DP_MAX_RANKS; ++r)
+          if (r < c.world) st_peer_v4(reinterpret_cast<uint4*>(a.out[r]) + v, packed);
+      }
     }
   }
   rank_barrier(c, a.channel);  // pushes visible everywhere; peers done reading my gradients

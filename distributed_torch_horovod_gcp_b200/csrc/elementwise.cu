@@ -71,20 +71,33 @@ __device__ __forceinline__ void block_reduce_to_global(float (&acc)[NACC][8], in
   }
 }
 
+// B200 needs >= ~64 KB in flight per SM to saturate HBM3e (6.5 TB/s x ~1 us): every kernel below
+// issues UNROLL independent 128-bit loads per thread per input before consuming any of them.
+__device__ __forceinline__ uint4 ld_or_zero(const uint4* p, long long i, long long n) {
+  return i < n ? ldg_stream(p + i) : make_uint4(0, 0, 0, 0);
+}
+
 // ---- forward statistics: sum[c], sumsq[c] -------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) bn_stats_kernel(const uint4* __restrict__ x, float* sum,
-                                                           float* sumsq, long long nvec, int V) {
+__global__ void __launch_bounds__(THREADS, 4) bn_stats_kernel(const uint4* __restrict__ x, float* sum,
+                                                              float* sumsq, long long nvec, int V) {
+  constexpr int U = 4;
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   const long long stride = (long long)gridDim.x * THREADS;
-  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < nvec; i += stride) {
-    float f[8];
-    unpack8(ldg_stream(x + i), f);
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < nvec; i += U * stride) {
+    uint4 raw[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0][j] += f[j];
-      acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
+    for (int u = 0; u < U; ++u) raw[u] = ld_or_zero(x, i + u * stride, nvec);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float f[8];
+      unpack8(raw[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += f[j];
+        acc[1][j] = fmaf(f[j], f[j], acc[1][j]);
+      }
     }
   }
   float* outs[2] = {sum, sumsq};
@@ -125,11 +138,12 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const v
 }
 
 // ---- forward apply: y = relu(x*a + b + residual) ---------------------------------------------------
-__global__ void __launch_bounds__(THREADS) bn_apply_kernel(const uint4* __restrict__ x,
-                                                           const uint4* __restrict__ res, uint4* y,
-                                                           const float* __restrict__ a,
-                                                           const float* __restrict__ b, long long nvec,
-                                                           int V, int relu) {
+__global__ void __launch_bounds__(THREADS, 4) bn_apply_kernel(const uint4* __restrict__ x,
+                                                              const uint4* __restrict__ res, uint4* y,
+                                                              const float* __restrict__ a,
+                                                              const float* __restrict__ b, long long nvec,
+                                                              int V, int relu) {
+  constexpr int U = 4;
   const long long stride = (long long)gridDim.x * THREADS;
   const long long i0 = (long long)blockIdx.x * THREADS + threadIdx.x;
   if (i0 >= nvec) return;
@@ -140,30 +154,42 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const uint4* __restri
     av[j] = a[cg * 8 + j];
     bv[j] = b[cg * 8 + j];
   }
-  for (long long i = i0; i < nvec; i += stride) {
-    float f[8];
-    unpack8(ldg_stream(x + i), f);
+  for (long long i = i0; i < nvec; i += U * stride) {
+    uint4 rx[U], rr[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], av[j], bv[j]);
+    for (int u = 0; u < U; ++u) rx[u] = ld_or_zero(x, i + u * stride, nvec);
     if (res) {
-      float r[8];
-      unpack8(ldg_stream(res + i), r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += r[j];
+      for (int u = 0; u < U; ++u) rr[u] = ld_or_zero(res, i + u * stride, nvec);
     }
-    if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride >= nvec) break;
+      float f[8];
+      unpack8(rx[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], av[j], bv[j]);
+      if (res) {
+        float r[8];
+        unpack8(rr[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      y[i + u * stride] = pack8(f);
     }
-    y[i] = pack8(f);
   }
 }
 
 // ---- backward reduce: sum_dy[c], sum_dy_xhat[c] (dy masked by y > 0 when relu) ----------------------
-__global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(
+__global__ void __launch_bounds__(THREADS, 4) bn_bwd_reduce_kernel(
     const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y,
     const float* __restrict__ mean, const float* __restrict__ invstd, float* sum_dy, float* sum_dy_xhat,
     long long nvec, int V, int relu) {
+  constexpr int U = 2;
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
@@ -178,20 +204,30 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(
       iv[j] = invstd[cg * 8 + j];
     }
   }
-  for (long long i = i0; i < nvec; i += stride) {
-    float g[8], xv[8];
-    unpack8(ldg_stream(dy + i), g);
-    unpack8(ldg_stream(x + i), xv);
-    if (relu) {
-      float yv[8];
-      unpack8(ldg_stream(y + i), yv);
+  for (long long i = i0; i < nvec; i += U * stride) {
+    uint4 rg[U], rx[U], ry[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+    for (int u = 0; u < U; ++u) {
+      rg[u] = ld_or_zero(dy, i + u * stride, nvec);
+      rx[u] = ld_or_zero(x, i + u * stride, nvec);
+      if (relu) ry[u] = ld_or_zero(y, i + u * stride, nvec);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0][j] += g[j];
-      acc[1][j] = fmaf(g[j], (xv[j] - mv[j]) * iv[j], acc[1][j]);
+    for (int u = 0; u < U; ++u) {
+      float g[8], xv[8];
+      unpack8(rg[u], g);
+      unpack8(rx[u], xv);
+      if (relu) {
+        float yv[8];
+        unpack8(ry[u], yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += g[j];
+        acc[1][j] = fmaf(g[j], (xv[j] - mv[j]) * iv[j], acc[1][j]);
+      }
     }
   }
   float* outs[2] = {sum_dy, sum_dy_xhat};
@@ -199,11 +235,12 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(
 }
 
 // ---- backward apply: dx = a*(dz - sum_dy/M - xhat*sum_dy_xhat/M), dres = dz ------------------------
-__global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(
+__global__ void __launch_bounds__(THREADS, 4) bn_bwd_apply_kernel(
     const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y, uint4* dx,
     uint4* dres, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ scale_a, const float* __restrict__ sum_dy,
     const float* __restrict__ sum_dy_xhat, float inv_count, long long nvec, int V, int relu) {
+  constexpr int U = 2;
   const long long stride = (long long)gridDim.x * THREADS;
   const long long i0 = (long long)blockIdx.x * THREADS + threadIdx.x;
   if (i0 >= nvec) return;
@@ -218,23 +255,112 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(
     k1[j] = sum_dy[c] * inv_count;
     k2[j] = sum_dy_xhat[c] * inv_count;
   }
-  for (long long i = i0; i < nvec; i += stride) {
-    float g[8], xv[8], o[8];
-    unpack8(ldg_stream(dy + i), g);
-    unpack8(ldg_stream(x + i), xv);
-    if (relu) {
-      float yv[8];
-      unpack8(ldg_stream(y + i), yv);
+  for (long long i = i0; i < nvec; i += U * stride) {
+    uint4 rg[U], rx[U], ry[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+    for (int u = 0; u < U; ++u) {
+      rg[u] = ld_or_zero(dy, i + u * stride, nvec);
+      rx[u] = ld_or_zero(x, i + u * stride, nvec);
+      if (relu) ry[u] = ld_or_zero(y, i + u * stride, nvec);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xhat = (xv[j] - mv[j]) * iv[j];
-      o[j] = sc[j] * (g[j] - k1[j] - xhat * k2[j]);
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride >= nvec) break;
+      float g[8], xv[8], o[8];
+      unpack8(rg[u], g);
+      unpack8(rx[u], xv);
+      if (relu) {
+        float yv[8];
+        unpack8(ry[u], yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = (xv[j] - mv[j]) * iv[j];
+        o[j] = sc[j] * (g[j] - k1[j] - xhat * k2[j]);
+      }
+      dx[i + u * stride] = pack8(o);
+      if (dres) dres[i + u * stride] = pack8(g);
     }
-    dx[i] = pack8(o);
-    if (dres) dres[i] = pack8(g);
+  }
+}
+
+// ---- 3x3 stride-2 pad-1 max pooling, NHWC bf16 -------------------------------------------------------
+// forward stores the arg-max tap (0..8) as one byte per output element; backward is a gather: every
+// input pixel looks at the <= 4 windows that cover it and takes dy where it was the arg-max (no atomics).
+__global__ void __launch_bounds__(THREADS) maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* y,
+                                                              uint2* __restrict__ idx, int N, int H, int W,
+                                                              int OH, int OW, int V) {
+  const long long total = (long long)N * OH * OW * V;
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < total;
+       i += (long long)gridDim.x * THREADS) {
+    const int cv = (int)(i % V);
+    long long t = i / V;
+    const int ow = (int)(t % OW); t /= OW;
+    const int oh = (int)(t % OH);
+    const int n = (int)(t / OH);
+    float best[8];
+    uint32_t arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; arg[j] = 0; }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * 2 - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * 2 - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        float f[8];
+        unpack8(x[(((long long)n * H + ih) * W + iw) * V + cv], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (f[j] > best[j]) { best[j] = f[j]; arg[j] = kh * 3 + kw; }
+      }
+    }
+    y[i] = pack8(best);
+    uint2 packed;
+    packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+    packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+    idx[i] = packed;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) maxpool_bwd_kernel(const uint4* __restrict__ dy,
+                                                              const uint2* __restrict__ idx, uint4* dx,
+                                                              int N, int H, int W, int OH, int OW, int V) {
+  const long long total = (long long)N * H * W * V;
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < total;
+       i += (long long)gridDim.x * THREADS) {
+    const int cv = (int)(i % V);
+    long long t = i / V;
+    const int iw = (int)(t % W); t /= W;
+    const int ih = (int)(t % H);
+    const int n = (int)(t / H);
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    // windows (oh, ow) with oh*2-1 <= ih <= oh*2+1
+    const int oh0 = max((ih - 1 + 1) / 2, 0), oh1 = min((ih + 1) / 2, OH - 1);
+    const int ow0 = max((iw - 1 + 1) / 2, 0), ow1 = min((iw + 1) / 2, OW - 1);
+    for (int oh = oh0; oh <= oh1; ++oh) {
+      const int kh = ih - (oh * 2 - 1);
+      for (int ow = ow0; ow <= ow1; ++ow) {
+        const int kw = iw - (ow * 2 - 1);
+        const uint32_t tap = (uint32_t)(kh * 3 + kw);
+        const long long o = (((long long)n * OH + oh) * OW + ow) * V + cv;
+        const uint2 a = idx[o];
+        float d[8];
+        unpack8(dy[o], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
+          if (aj == tap) g[j] += d[j];
+        }
+      }
+    }
+    dx[i] = pack8(g);
   }
 }
 
@@ -245,8 +371,8 @@ int fail(const char* what, cudaError_t e) {
 }
 
 int grid_for(long long nvec, int V) {
-  long long blocks = (nvec + THREADS * 4 - 1) / (THREADS * 4);
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  long long blocks = (nvec + THREADS * 8 - 1) / (THREADS * 8);
+  if (blocks > 148 * 6) blocks = 148 * 6;
   if (blocks < 1) blocks = 1;
   // total threads must be a multiple of V (V is a power of two <= 256 => always true)
   return (int)blocks;
@@ -269,7 +395,7 @@ int b200dp_bn_supported(int C) { return shape_ok(C) ? 1 : 0; }
 int b200dp_bn_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta,
                   float* stats, float* mean, float* invstd, float* a, float* b, void* running_mean,
                   void* running_var, long long M, int C, float eps, float momentum, int relu,
-                  int param_bf16, unsigned long long stream) {
+                  int param_bf16, int have_stats, unsigned long long stream) {
   if (!shape_ok(C)) {
     snprintf(g_err, sizeof(g_err), "unsupported channel count %d", C);
     return -1;
@@ -277,10 +403,13 @@ int b200dp_bn_fwd(const void* x, const void* res, void* y, const void* gamma, co
   cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
   const int V = C / 8;
   const long long nvec = M * V;
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C, st);
-  if (e != cudaSuccess) return fail("memset", e);
+  cudaError_t e = cudaSuccess;
   const int grid = grid_for(nvec, V);
-  bn_stats_kernel<<<grid, THREADS, 0, st>>>((const uint4*)x, stats, stats + C, nvec, V);
+  if (!have_stats) {   // otherwise `stats` was accumulated by the producing GEMM's epilogue
+    e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C, st);
+    if (e != cudaSuccess) return fail("memset", e);
+    bn_stats_kernel<<<grid, THREADS, 0, st>>>((const uint4*)x, stats, stats + C, nvec, V);
+  }
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, stats + C, gamma, beta, mean, invstd, a, b,
                                                       running_mean, running_var, (float)M, eps, momentum, C,
                                                       param_bf16);
@@ -322,6 +451,35 @@ int b200dp_bn_bwd(const void* dy, const void* x, const void* y, void* dx, void* 
                                                 sums + C, 1.0f / (float)M, nvec, V, relu);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail("bn_bwd launch", e);
+  return 0;
+}
+
+// 3x3/s2/p1 max-pool over NHWC bf16; idx: [N*OH*OW*C] bytes (arg-max tap per output element).
+int b200dp_maxpool_fwd(const void* x, void* y, void* idx, int N, int H, int W, int C,
+                       unsigned long long stream) {
+  if (C % 8) return -1;
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1, V = C / 8;
+  const long long total = (long long)N * OH * OW * V;
+  int grid = (int)((total + THREADS - 1) / THREADS);
+  if (grid > 148 * 16) grid = 148 * 16;
+  maxpool_fwd_kernel<<<grid, THREADS, 0, (cudaStream_t)(uintptr_t)stream>>>((const uint4*)x, (uint4*)y,
+                                                                             (uint2*)idx, N, H, W, OH, OW, V);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("maxpool_fwd launch", e);
+  return 0;
+}
+
+int b200dp_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, int W, int C,
+                       unsigned long long stream) {
+  if (C % 8) return -1;
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1, V = C / 8;
+  const long long total = (long long)N * H * W * V;
+  int grid = (int)((total + THREADS - 1) / THREADS);
+  if (grid > 148 * 16) grid = 148 * 16;
+  maxpool_bwd_kernel<<<grid, THREADS, 0, (cudaStream_t)(uintptr_t)stream>>>((const uint4*)dy, (const uint2*)idx,
+                                                                             (uint4*)dx, N, H, W, OH, OW, V);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("maxpool_bwd launch", e);
   return 0;
 }
 

@@ -41,6 +41,8 @@ struct GemmParams {
   const void* bias_f32;    // fp32 [N] or nullptr
   const void* residual;    // bf16 [M, ldc] or nullptr (added after act; or `aux` for act 3/4)
   void* preact;            // optional bf16 [M, ldc]: pre-activation values (saved for backward)
+  float* col_stats;        // optional fp32 [2*N]: += per-column sum | sum of squares of the bf16 output
+                           // (BatchNorm statistics fused into the producing GEMM; out_mode 0 only)
   float alpha;
 };
 
@@ -320,23 +322,71 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
+    // fused BN statistics: lane l owns column (chunk*32 + l) of the current n-block; partial sums
+    // stay in registers across all tiles of that n-block and are flushed with one atomic each.
+    float st_sum[BN / 32], st_sq[BN / 32];
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) st_sum[i] = st_sq[i] = 0.f;
+    int st_n_idx = -1;
+    auto flush_stats = [&]() {
+      if (p.col_stats == nullptr || st_n_idx < 0) return;
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) {
+        const int col = st_n_idx + i * 32 + lane;
+        if (col < p.N) {
+          atomicAdd(p.col_stats + col, st_sum[i]);
+          atomicAdd(p.col_stats + p.N + col, st_sq[i]);
+        }
+        st_sum[i] = st_sq[i] = 0.f;
+      }
+    };
     for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
       const int tile = w % tiles, split = w / tiles;
       const int m_idx = (tile % p.num_m_blocks) * BLOCK_M;
       const int n_idx = (tile / p.num_m_blocks) * BN;
+      if (n_idx != st_n_idx) {
+        flush_stats();
+        st_n_idx = n_idx;
+      }
       const int kb0 = split * kb_per_split;
       const bool has_k = min(kb0 + kb_per_split, p.num_k_blocks) > kb0;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m_idx + q * 32 + lane;
       const bool row_ok = row < p.M;
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
         tc_ld_32x32b_x32(taddr, r);
         tc_wait_ld();
         const int col0 = n_idx + c0;
+        if (p.col_stats != nullptr && col0 < p.N) {
+          // warp-collective: every lane participates (rows >= M hold exact zeros: TMA zero-fill)
+          float a[32], b2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[i]) * p.alpha));
+            a[i] = x;
+            b2[i] = x * x;
+          }
+          // butterfly reduce-scatter over the 32 lanes: after 5 steps lane l holds column l
+#pragma unroll
+          for (int half = 16; half >= 1; half >>= 1) {
+            const bool up = (lane & half) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+              const float sa = up ? a[i] : a[i + half];
+              const float sb = up ? b2[i] : b2[i + half];
+              const float ra = __shfl_xor_sync(0xffffffffu, sa, half);
+              const float rb = __shfl_xor_sync(0xffffffffu, sb, half);
+              a[i] = (up ? a[i + half] : a[i]) + ra;
+              b2[i] = (up ? b2[i + half] : b2[i]) + rb;
+            }
+          }
+          st_sum[c0 / 32] += a[0];
+          st_sq[c0 / 32] += b2[0];
+        }
         if (!row_ok || col0 >= p.N || !has_k) continue;
         float v[32];
 #pragma unroll
@@ -412,6 +462,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    flush_stats();
   }
 
   tc_fence_before();
@@ -495,7 +546,7 @@ const char* b200dp_gemm_last_error() { return g_err; }
 // 16-byte aligned base pointers and leading dimensions.
 int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                      int a_mn, int b_mn, const void* bias_bf16, const void* bias_f32, const void* residual,
-                     void* preact, int act, int out_mode, float alpha, int splits, int block_n, int max_ctas,
+                     void* preact, float* col_stats, int act, int out_mode, float alpha, int splits, int block_n, int max_ctas,
                      unsigned long long stream) {
   if (ensure_init()) return -1;
   if (M <= 0 || N <= 0 || K <= 0) return fail("bad shape");
@@ -519,6 +570,7 @@ int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K,
   }
   p.act = act; p.out_mode = out_mode; p.C = C; p.bias = bias_bf16; p.bias_f32 = bias_f32;
   p.residual = residual; p.preact = preact; p.alpha = alpha;
+  p.col_stats = (out_mode == 0) ? col_stats : nullptr;
   CUtensorMap ma, mb;
   if (a_mn ? make_map(&ma, A, K, M, lda, BLOCK_K) : make_map(&ma, A, M, K, lda, BLOCK_M)) return -1;
   if (b_mn ? make_map(&mb, B, K, N, ldb, BLOCK_K) : make_map(&mb, B, N, K, ldb, BN)) return -1;

@@ -7,7 +7,7 @@ from typing import Dict
 from . import gemm as _gemm
 from . import bn as _bn
 from .gemm import linear  # noqa: F401  (re-exported as kernels.linear)
-from .bn import conv_bn_act, bn_act  # noqa: F401
+from .bn import conv_bn_act, bn_act, max_pool_3x3_s2  # noqa: F401
 
 
 def register(lib, have: Dict[str, bool]) -> None:

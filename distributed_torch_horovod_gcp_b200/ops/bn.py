@@ -23,13 +23,17 @@ def register(lib, have):
         return
     _lib = lib
     vp, i, f, ll, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_uint64
-    lib.b200dp_bn_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, i, i, u64]
+    lib.b200dp_bn_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, i, i, i, u64]
     lib.b200dp_bn_apply.argtypes = [vp, vp, vp, vp, vp, ll, i, i, u64]
     lib.b200dp_bn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, i, u64]
     lib.b200dp_bn_supported.argtypes = [i]
     lib.b200dp_ew_last_error.restype = ctypes.c_char_p
     have["bn_act"] = True
     have["conv_bn_act"] = True
+    if hasattr(lib, "b200dp_maxpool_fwd"):
+        lib.b200dp_maxpool_fwd.argtypes = [vp, vp, vp, i, i, i, i, u64]
+        lib.b200dp_maxpool_bwd.argtypes = [vp, vp, vp, i, i, i, i, u64]
+        have["max_pool_3x3_s2"] = True
 
 
 def _ck(rc):
@@ -50,13 +54,16 @@ class _BNActFn(torch.autograd.Function):
     """Training-mode BN over NHWC bf16 with fused residual add and ReLU."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, relu, eps, momentum):
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, relu, eps, momentum,
+                stats_in=None):
         N, C, H, W = x.shape
         M = N * H * W
         dev = x.device
         y = torch.empty_like(x, memory_format=torch.channels_last)
         ws = torch.empty(6 * C, dtype=torch.float32, device=dev)
         stats, mean, invstd, a, b = ws[:2 * C], ws[2 * C:3 * C], ws[3 * C:4 * C], ws[4 * C:5 * C], ws[5 * C:]
+        if stats_in is not None:
+            stats = stats_in              # accumulated by the producing GEMM's epilogue
         pbf16 = int(gamma.dtype == torch.bfloat16)
         st = torch.cuda.current_stream(dev).cuda_stream
         _ck(_lib.b200dp_bn_fwd(x.data_ptr(), residual.data_ptr() if residual is not None else None,
@@ -64,8 +71,9 @@ class _BNActFn(torch.autograd.Function):
                                mean.data_ptr(), invstd.data_ptr(), a.data_ptr(), b.data_ptr(),
                                running_mean.data_ptr() if running_mean is not None else None,
                                running_var.data_ptr() if running_var is not None else None,
-                               M, C, float(eps), float(momentum), int(relu), pbf16, st))
-        counters.bump("bn_fwd", 3)
+                               M, C, float(eps), float(momentum), int(relu), pbf16,
+                               int(stats_in is not None), st))
+        counters.bump("bn_fwd", 2 if stats_in is not None else 3)
         ctx.save_for_backward(x, y if relu else None, mean, invstd, a)
         ctx.relu, ctx.has_res, ctx.pdtype = relu, residual is not None, gamma.dtype
         return y
@@ -91,10 +99,11 @@ class _BNActFn(torch.autograd.Function):
         dgamma = sums[C:].to(ctx.pdtype)
         if ctx.has_res and dres is None:
             dres = dy                       # no ReLU: the residual branch gets dy unchanged
-        return dx, dgamma, dbeta, None, None, dres, None, None, None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
 
 
-def bn_act(x, bn: torch.nn.BatchNorm2d, relu: bool, residual: Optional[torch.Tensor] = None):
+def bn_act(x, bn: torch.nn.BatchNorm2d, relu: bool, residual: Optional[torch.Tensor] = None,
+           stats: Optional[torch.Tensor] = None):
     if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
         residual = residual.contiguous(memory_format=torch.channels_last)
     if bn.training:
@@ -102,7 +111,7 @@ def bn_act(x, bn: torch.nn.BatchNorm2d, relu: bool, residual: Optional[torch.Ten
             bn.num_batches_tracked.add_(1)
         mom = bn.momentum if bn.momentum is not None else 0.1
         return _BNActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
-                              relu, bn.eps, mom)
+                              relu, bn.eps, mom, stats)
     # inference: frozen statistics -> one fused apply pass
     a = (bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps))
     b = bn.bias.float() - bn.running_mean.float() * a
@@ -115,27 +124,77 @@ def bn_act(x, bn: torch.nn.BatchNorm2d, relu: bool, residual: Optional[torch.Ten
     return y
 
 
-def conv2d(x, conv: torch.nn.Conv2d):
-    """Convolution of an NHWC bf16 activation; 1x1/stride-1 -> tcgen05 GEMM."""
+_FUSE_STATS = os.environ.get("B200DP_FUSE_BN_STATS", "1") == "1"
+
+
+def _is_gemm_conv(x, conv) -> bool:
     w = conv.weight
-    if (_USE_GEMM_1X1 and _gemm._lib is not None and conv.kernel_size == (1, 1)
+    return (_USE_GEMM_1X1 and _gemm._lib is not None and conv.kernel_size == (1, 1)
             and conv.stride == (1, 1) and conv.padding == (0, 0) and conv.groups == 1
             and conv.bias is None and w.dtype == torch.bfloat16 and _nhwc_ok(x)
-            and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0):
+            and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0)
+
+
+def conv2d(x, conv: torch.nn.Conv2d, col_stats: Optional[torch.Tensor] = None):
+    """Convolution of an NHWC bf16 activation; 1x1/stride-1 -> tcgen05 GEMM (optionally
+    accumulating the BatchNorm statistics of its output in the epilogue)."""
+    w = conv.weight
+    if _is_gemm_conv(x, conv):
         N, C, H, W = x.shape
         x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, C)             # view: NHWC rows
-        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C))              # [M, Cout]
+        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C), col_stats=col_stats)   # [M, Cout]
         return y2.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2)      # logical NCHW, NHWC memory
     return F.conv2d(x, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
 def conv_bn_act(x, conv, bn, relu: bool, residual=None):
-    y = conv2d(x, conv)
+    Cout = conv.weight.shape[0]
+    fuse = (_FUSE_STATS and bn.training and bn.weight is not None and _is_gemm_conv(x, conv)
+            and bool(_lib.b200dp_bn_supported(Cout)))
+    stats = torch.zeros(2 * Cout, dtype=torch.float32, device=x.device) if fuse else None
+    y = conv2d(x, conv, stats)
     C = y.shape[1]
     if bn_supported(y, C) and bn.weight is not None and \
             (residual is None or residual.dtype == torch.bfloat16):
-        return bn_act(y, bn, relu, residual)
+        return bn_act(y, bn, relu, residual, stats)
     y = bn(y)
     if residual is not None:
         y = y + residual
     return F.relu(y) if relu else y
+
+
+class _MaxPoolFn(torch.autograd.Function):
+    """3x3 / stride 2 / pad 1 max-pool on NHWC bf16 (byte arg-max saved; gather backward)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, C, H, W = x.shape
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((N, C, OH, OW), dtype=x.dtype, device=x.device,
+                        memory_format=torch.channels_last)
+        idx = torch.empty(N * OH * OW * C, dtype=torch.uint8, device=x.device)
+        _ck(_lib.b200dp_maxpool_fwd(x.data_ptr(), y.data_ptr(), idx.data_ptr(), N, H, W, C,
+                                    torch.cuda.current_stream(x.device).cuda_stream))
+        counters.bump("maxpool_fwd")
+        ctx.save_for_backward(idx)
+        ctx.shape = (N, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        N, C, H, W = ctx.shape
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((N, C, H, W), dtype=dy.dtype, device=dy.device,
+                         memory_format=torch.channels_last)
+        _ck(_lib.b200dp_maxpool_bwd(dy.data_ptr(), idx.data_ptr(), dx.data_ptr(), N, H, W, C,
+                                    torch.cuda.current_stream(dy.device).cuda_stream))
+        counters.bump("maxpool_bwd")
+        return dx
+
+
+def max_pool_3x3_s2(x):
+    if _nhwc_ok(x) and x.shape[1] % 8 == 0:
+        return _MaxPoolFn.apply(x)
+    return F.max_pool2d(x, kernel_size=3, stride=2, padding=1)

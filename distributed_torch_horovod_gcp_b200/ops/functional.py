@@ -44,6 +44,9 @@ def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool = True,
 
 
 def max_pool_3x3_s2(x):
+    k = _kernels(x)
+    if k is not None and k.has("max_pool_3x3_s2"):
+        return k.max_pool_3x3_s2(x)
     return F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
 
 

@@ -338,7 +338,7 @@ class SymmRuntime:
         work = nbytes if algo == ALGO_ONESHOT else nbytes // max(self.world, 1)
         per_block = 512 * 16 * 2
         b = max(1, min((work + per_block - 1) // per_block, MAX_BLOCKS))
-        cap = self.max_blocks or (32 if algo == ALGO_ONESHOT else (24 if algo == ALGO_NVLS else 48))
+        cap = self.max_blocks or (32 if algo == ALGO_ONESHOT else (48 if algo == ALGO_NVLS else 64))
         return int(min(b, cap))
 
     # ------------------------------------------------------------------ launches
@@ -381,6 +381,46 @@ class SymmRuntime:
         ev = torch.cuda.Event()
         ev.record(stream)
         return ev
+
+    def prepare_allreduce(self, t: torch.Tensor, scale: float = 1.0, algo: Optional[int] = None):
+        """Pre-build the launch arguments for an in-place allreduce of a symmetric tensor and
+        return a zero-argument callable that only does the ctypes launch on the current stream
+        (host overhead ~2 us instead of ~12 us; used by benchmarks and tight loops)."""
+        loc = self.find(t)
+        es = t.element_size()
+        assert loc is not None and loc[1] % 16 == 0 and t.numel() % (16 // es) == 0 and \
+            t.is_contiguous(), "prepare_allreduce needs a 16B-aligned contiguous symmetric tensor"
+        buf, off = loc
+        nbytes = t.numel() * es
+        a = ARArgs()
+        ptrs = buf.ptrs_at(off)
+        for r in range(self.world):
+            a.inp[r] = ptrs[r]
+            a.out[r] = ptrs[r]
+        a.n, a.scale, a.channel = t.numel(), float(scale), CH_USER
+        a.h.kind = OPT_NONE
+        algo = self.pick_algo(nbytes, need_mc=buf.mc_ptr != 0) if algo is None else algo
+        if algo == ALGO_NVLS and buf.mc_ptr == 0:
+            algo = ALGO_TWOSHOT
+        if algo == ALGO_NVLS:
+            a.in_mc = a.out_mc = buf.mc_ptr + off
+        if algo == ALGO_ONESHOT:
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            a.scratch, a.copy_back = scratch.data_ptr(), 1
+        else:
+            scratch = None
+        blocks = self.pick_blocks(algo, nbytes)
+        code = _DTYPE_CODE[t.dtype]
+        fn, ctx_ref, a_ref = self.lib.b200dp_comm_allreduce, ctypes.byref(self.ctx), ctypes.byref(a)
+        dev = self.device
+
+        def launch(_keep=(a, scratch, t)):
+            rc = fn(ctx_ref, a_ref, algo, code, blocks, 512, torch.cuda.current_stream(dev).cuda_stream)
+            if rc != 0:
+                raise RuntimeError((self.lib.b200dp_comm_last_error() or b"").decode())
+        launch.algo = ALGO_NAMES[algo]
+        launch.blocks = blocks
+        return launch
 
     def _ar_symm(self, buf: SymmBuffer, off: int, numel: int, dtype, scale, stream, algo,
                  user: bool = False):

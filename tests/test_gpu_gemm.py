@@ -169,3 +169,35 @@ def test_resnet50_kernels_vs_reference_ops():
     print("grad rel err vs fp32: fc", g_ref, g_ker, "layer1.0.conv1", c_ref, c_ker)
     assert g_ker < max(2.0 * g_ref, 0.05)
     assert c_ker < max(2.5 * c_ref, 0.1)
+
+
+def test_maxpool_matches_torch():
+    from distributed_torch_horovod_gcp_b200.ops import kernels
+    assert kernels.has("max_pool_3x3_s2")
+    torch.manual_seed(6)
+    for (N, C, H, W) in [(4, 64, 112, 112), (2, 16, 9, 7)]:
+        x = torch.randn(N, C, H, W, device="cuda").to(torch.bfloat16).contiguous(
+            memory_format=torch.channels_last).requires_grad_(True)
+        xr = x.detach().float().requires_grad_(True)
+        y = kernels.max_pool_3x3_s2(x)
+        yr = torch.nn.functional.max_pool2d(xr, 3, 2, 1)
+        assert torch.equal(y.float(), yr)
+        g = torch.randn_like(y)
+        y.backward(g)
+        yr.backward(g.float())
+        # ties are measure-zero for random inputs; bf16 accumulation of <= 4 terms
+        assert _rel(x.grad, xr.grad) < 1e-2
+
+
+def test_gemm_fused_bn_stats():
+    g = _k()
+    torch.manual_seed(7)
+    for (M, N, K) in [(5000, 256, 64), (1000, 512, 128), (130, 64, 256)]:
+        a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+        b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.1
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        st = torch.zeros(2 * N, device="cuda", dtype=torch.float32)
+        g.gemm(a, b, out, M, N, K, col_stats=st)
+        of = out.float()
+        assert _rel(st[:N] + 1.0, of.sum(0) + 1.0) < 2e-3
+        assert _rel(st[N:], (of * of).sum(0)) < 2e-3
