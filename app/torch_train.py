@@ -57,6 +57,10 @@ def parse_args(argv=None):
     p.add_argument("--steps-per-epoch", type=int, default=int(env("B200DP_STEPS_PER_EPOCH", "20")),
                    help="synthetic image models only")
     p.add_argument("--no-validate", action="store_true")
+    p.add_argument("--cuda-graph", action="store_true",
+                   default=env("B200DP_CUDA_GRAPH", "0") == "1",
+                   help="capture the whole training step (fwd+bwd+fused allreduce/update) in one "
+                        "CUDA graph; B200-first answer for the launch-bound LSTM config")
     p.add_argument("--data", default=env("B200DP_DATA", "data_es.csv"))
     return p.parse_args(argv)
 
@@ -157,6 +161,8 @@ if __name__ == "__main__":
         optimizer = torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9, weight_decay=1e-4)
         loss_fn = nn.CrossEntropyLoss()
 
+    if args.cuda_graph and use_cuda:
+        os.environ.setdefault("B200DP_FUSED_SINGLE", "1")    # graph capture needs the fused update
     optimizer = hvd.DistributedOptimizer(optimizer, named_parameters=model.named_parameters())
 
     model.to(_DEVICE)
@@ -164,19 +170,32 @@ if __name__ == "__main__":
 
     hvd.broadcast_parameters(model.state_dict(), root_rank=0)
 
+    def train_step(inputs, labels):
+        pred = model(inputs)
+        loss = loss_fn(pred.float(), labels)
+        # Getting gradients w.r.t. parameters
+        loss.backward()
+        # Updating parameters
+        optimizer.step()
+        optimizer.zero_grad()
+        return loss.detach()
+
+    graphed = {}
+
     def train(epoch, device):
         loss = None
         for i, data in enumerate(train_loader):
             # move x and y to the device (no-op when the loader is device resident)
             inputs = data[0].to(_DEVICE, non_blocking=True)
             labels = data[1].to(_DEVICE, non_blocking=True)
-            pred = model(inputs)
-            loss = loss_fn(pred.float(), labels)
-            # Getting gradients w.r.t. parameters
-            loss.backward()
-            # Updating parameters
-            optimizer.step()
-            optimizer.zero_grad()
+            if args.cuda_graph and use_cuda and getattr(optimizer, "fused_engine", None) is not None:
+                key = (tuple(inputs.shape), tuple(labels.shape))
+                if key not in graphed and len(graphed) < 2:
+                    from distributed_torch_horovod_gcp_b200.utils.graph import GraphedStep
+                    graphed[key] = GraphedStep(train_step, [inputs, labels])
+                loss = graphed[key](inputs, labels) if key in graphed else train_step(inputs, labels)
+            else:
+                loss = train_step(inputs, labels)
             if args.max_steps and i + 1 >= args.max_steps:
                 break
         # write stats if running on main

@@ -46,30 +46,31 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 // group i % V.  The total thread count is a multiple of V, so a thread always owns ONE channel
 // group and accumulates NACC x 8 partial sums in registers; threads of a block that share a group
 // are combined through shared memory and the block issues one atomicAdd per (channel, quantity).
-template <int NACC>
+template <int NACC, int NT>
 __device__ __forceinline__ void block_reduce_to_global(float (&acc)[NACC][8], int V, float* const* outs) {
-  __shared__ float sm[THREADS][8 + 1];
+  __shared__ float sm[NT][8 + 1];
   const int tid = threadIdx.x;
-  const int groups = THREADS / V;      // threads per channel group inside this block (>=1)
+  const int groups = NT / V;      // threads per channel group inside this block (>=1)
 #pragma unroll
   for (int q = 0; q < NACC; ++q) {
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 8; ++j) sm[tid][j] = acc[q][j];
     __syncthreads();
-    if (tid < V) {
-      float s[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s[j] = 0.f;
-      for (int g = 0; g < groups; ++g) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s[j] += sm[tid + g * V][j];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(outs[q] + tid * 8 + j, s[j]);
+    // V*8 channel sums, each over `groups` partials: spread over all threads (8 per group)
+    for (int item = tid; item < V * 8; item += NT) {
+      const int g0 = item >> 3, j = item & 7;
+      float s = 0.f;
+      for (int g = 0; g < groups; ++g) s += sm[g0 + g * V][j];
+      atomicAdd(outs[q] + g0 * 8 + j, s);
     }
   }
 }
+
+// Reduction kernels run ONE 1024-thread block per SM: same-address fp32 atomics serialise in L2
+// (~40 ns each), so the number of blocks — not the data size — set the tail of the first version
+// (888 blocks -> ~45 us per launch; 148 blocks -> ~7 us).
+constexpr int RTHREADS = 1024;
 
 // B200 needs >= ~64 KB in flight per SM to saturate HBM3e (6.5 TB/s x ~1 us): every kernel below
 // issues UNROLL independent 128-bit loads per thread per input before consuming any of them.
@@ -78,14 +79,14 @@ __device__ __forceinline__ uint4 ld_or_zero(const uint4* p, long long i, long lo
 }
 
 // ---- forward statistics: sum[c], sumsq[c] -------------------------------------------------------
-__global__ void __launch_bounds__(THREADS, 4) bn_stats_kernel(const uint4* __restrict__ x, float* sum,
-                                                              float* sumsq, long long nvec, int V) {
-  constexpr int U = 4;
+__global__ void __launch_bounds__(RTHREADS, 1) bn_stats_kernel(const uint4* __restrict__ x, float* sum,
+                                                               float* sumsq, long long nvec, int V) {
+  constexpr int U = 8;
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-  const long long stride = (long long)gridDim.x * THREADS;
-  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < nvec; i += U * stride) {
+  const long long stride = (long long)gridDim.x * RTHREADS;
+  for (long long i = (long long)blockIdx.x * RTHREADS + threadIdx.x; i < nvec; i += U * stride) {
     uint4 raw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) raw[u] = ld_or_zero(x, i + u * stride, nvec);
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(THREADS, 4) bn_stats_kernel(const uint4* __res
     }
   }
   float* outs[2] = {sum, sumsq};
-  block_reduce_to_global<2>(acc, V, outs);
+  block_reduce_to_global<2, RTHREADS>(acc, V, outs);
 }
 
 // ---- finalize: mean/invstd, affine (a, b), running statistics ------------------------------------
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(THREADS, 4) bn_apply_kernel(const uint4* __res
                                                               const uint4* __restrict__ res, uint4* y,
                                                               const float* __restrict__ a,
                                                               const float* __restrict__ b, long long nvec,
-                                                              int V, int relu) {
+                                                              int V, int relu, uint8_t* __restrict__ mask) {
   constexpr int U = 4;
   const long long stride = (long long)gridDim.x * THREADS;
   const long long i0 = (long long)blockIdx.x * THREADS + threadIdx.x;
@@ -176,6 +177,12 @@ __global__ void __launch_bounds__(THREADS, 4) bn_apply_kernel(const uint4* __res
         for (int j = 0; j < 8; ++j) f[j] += r[j];
       }
       if (relu) {
+        if (mask) {       // 1 bit per element: the backward reads this instead of re-reading y
+          uint32_t m = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) m |= (f[j] > 0.f ? 1u : 0u) << j;
+          mask[i + u * stride] = (uint8_t)m;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
       }
@@ -185,58 +192,52 @@ __global__ void __launch_bounds__(THREADS, 4) bn_apply_kernel(const uint4* __res
 }
 
 // ---- backward reduce: sum_dy[c], sum_dy_xhat[c] (dy masked by y > 0 when relu) ----------------------
-__global__ void __launch_bounds__(THREADS, 4) bn_bwd_reduce_kernel(
-    const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y,
-    const float* __restrict__ mean, const float* __restrict__ invstd, float* sum_dy, float* sum_dy_xhat,
-    long long nvec, int V, int relu) {
+// Accumulates sum(dz) and sum(dz * (x - mean)); the invstd factor is applied when the sums are used.
+__global__ void __launch_bounds__(RTHREADS, 1) bn_bwd_reduce_kernel(
+    const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint8_t* __restrict__ mask,
+    const float* __restrict__ mean, float* sum_dy, float* sum_dy_xc, long long nvec, int V, int relu) {
   constexpr int U = 2;
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-  const long long stride = (long long)gridDim.x * THREADS;
-  const long long i0 = (long long)blockIdx.x * THREADS + threadIdx.x;
-  float mv[8], iv[8];
+  const long long stride = (long long)gridDim.x * RTHREADS;
+  const long long i0 = (long long)blockIdx.x * RTHREADS + threadIdx.x;
+  float mv[8];
   {
     const int cg = (int)(i0 % V);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      mv[j] = mean[cg * 8 + j];
-      iv[j] = invstd[cg * 8 + j];
-    }
+    for (int j = 0; j < 8; ++j) mv[j] = mean[cg * 8 + j];
   }
   for (long long i = i0; i < nvec; i += U * stride) {
-    uint4 rg[U], rx[U], ry[U];
+    uint4 rg[U], rx[U];
+    uint32_t rm[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       rg[u] = ld_or_zero(dy, i + u * stride, nvec);
       rx[u] = ld_or_zero(x, i + u * stride, nvec);
-      if (relu) ry[u] = ld_or_zero(y, i + u * stride, nvec);
+      rm[u] = (relu && i + u * stride < nvec) ? (uint32_t)__ldg(mask + i + u * stride) : 0xffu;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float g[8], xv[8];
       unpack8(rg[u], g);
       unpack8(rx[u], xv);
-      if (relu) {
-        float yv[8];
-        unpack8(ry[u], yv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
-      }
+      for (int j = 0; j < 8; ++j) g[j] = ((rm[u] >> j) & 1u) ? g[j] : 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         acc[0][j] += g[j];
-        acc[1][j] = fmaf(g[j], (xv[j] - mv[j]) * iv[j], acc[1][j]);
+        acc[1][j] = fmaf(g[j], xv[j] - mv[j], acc[1][j]);
       }
     }
   }
-  float* outs[2] = {sum_dy, sum_dy_xhat};
-  block_reduce_to_global<2>(acc, V, outs);
+  float* outs[2] = {sum_dy, sum_dy_xc};
+  block_reduce_to_global<2, RTHREADS>(acc, V, outs);
 }
 
 // ---- backward apply: dx = a*(dz - sum_dy/M - xhat*sum_dy_xhat/M), dres = dz ------------------------
 __global__ void __launch_bounds__(THREADS, 4) bn_bwd_apply_kernel(
-    const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ y, uint4* dx,
+    const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint8_t* __restrict__ mask, uint4* dx,
     uint4* dres, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ scale_a, const float* __restrict__ sum_dy,
     const float* __restrict__ sum_dy_xhat, float inv_count, long long nvec, int V, int relu) {
@@ -253,15 +254,16 @@ __global__ void __launch_bounds__(THREADS, 4) bn_bwd_apply_kernel(
     iv[j] = invstd[c];
     sc[j] = scale_a[c];      // gamma * invstd, saved by the forward
     k1[j] = sum_dy[c] * inv_count;
-    k2[j] = sum_dy_xhat[c] * inv_count;
+    k2[j] = sum_dy_xhat[c] * iv[j] * inv_count;   // reduce pass stored sum(dz*(x-mean))
   }
   for (long long i = i0; i < nvec; i += U * stride) {
-    uint4 rg[U], rx[U], ry[U];
+    uint4 rg[U], rx[U];
+    uint32_t rm[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       rg[u] = ld_or_zero(dy, i + u * stride, nvec);
       rx[u] = ld_or_zero(x, i + u * stride, nvec);
-      if (relu) ry[u] = ld_or_zero(y, i + u * stride, nvec);
+      rm[u] = (relu && i + u * stride < nvec) ? (uint32_t)__ldg(mask + i + u * stride) : 0xffu;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -269,12 +271,8 @@ __global__ void __launch_bounds__(THREADS, 4) bn_bwd_apply_kernel(
       float g[8], xv[8], o[8];
       unpack8(rg[u], g);
       unpack8(rx[u], xv);
-      if (relu) {
-        float yv[8];
-        unpack8(ry[u], yv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = yv[j] > 0.f ? g[j] : 0.f;
-      }
+      for (int j = 0; j < 8; ++j) g[j] = ((rm[u] >> j) & 1u) ? g[j] : 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xhat = (xv[j] - mv[j]) * iv[j];
@@ -370,6 +368,17 @@ int fail(const char* what, cudaError_t e) {
   return -1;
 }
 
+int g_sms = 0;
+int reduce_grid() {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
 int grid_for(long long nvec, int V) {
   long long blocks = (nvec + THREADS * 8 - 1) / (THREADS * 8);
   if (blocks > 148 * 6) blocks = 148 * 6;
@@ -380,7 +389,7 @@ int grid_for(long long nvec, int V) {
 
 bool shape_ok(int C) {
   const int V = C / 8;
-  return C % 8 == 0 && V >= 1 && V <= THREADS && (THREADS % V) == 0;
+  return C % 8 == 0 && V >= 1 && V <= THREADS && (THREADS % V) == 0;   // V | 256 | 1024
 }
 
 }  // namespace
@@ -395,7 +404,7 @@ int b200dp_bn_supported(int C) { return shape_ok(C) ? 1 : 0; }
 int b200dp_bn_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta,
                   float* stats, float* mean, float* invstd, float* a, float* b, void* running_mean,
                   void* running_var, long long M, int C, float eps, float momentum, int relu,
-                  int param_bf16, int have_stats, unsigned long long stream) {
+                  int param_bf16, int have_stats, void* relu_mask, unsigned long long stream) {
   if (!shape_ok(C)) {
     snprintf(g_err, sizeof(g_err), "unsupported channel count %d", C);
     return -1;
@@ -408,13 +417,13 @@ int b200dp_bn_fwd(const void* x, const void* res, void* y, const void* gamma, co
   if (!have_stats) {   // otherwise `stats` was accumulated by the producing GEMM's epilogue
     e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C, st);
     if (e != cudaSuccess) return fail("memset", e);
-    bn_stats_kernel<<<grid, THREADS, 0, st>>>((const uint4*)x, stats, stats + C, nvec, V);
+    bn_stats_kernel<<<reduce_grid(), RTHREADS, 0, st>>>((const uint4*)x, stats, stats + C, nvec, V);
   }
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, stats + C, gamma, beta, mean, invstd, a, b,
                                                       running_mean, running_var, (float)M, eps, momentum, C,
                                                       param_bf16);
   bn_apply_kernel<<<grid, THREADS, 0, st>>>((const uint4*)x, (const uint4*)res, (uint4*)y, a, b, nvec, V,
-                                            relu);
+                                            relu, (uint8_t*)relu_mask);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail("bn_fwd launch", e);
   return 0;
@@ -427,14 +436,15 @@ int b200dp_bn_apply(const void* x, const void* res, void* y, const float* a, con
   const int V = C / 8;
   const long long nvec = M * V;
   bn_apply_kernel<<<grid_for(nvec, V), THREADS, 0, (cudaStream_t)(uintptr_t)stream>>>(
-      (const uint4*)x, (const uint4*)res, (uint4*)y, a, b, nvec, V, relu);
+      (const uint4*)x, (const uint4*)res, (uint4*)y, a, b, nvec, V, relu, nullptr);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("bn_apply launch", e);
   return 0;
 }
 
 // sums: [2*C] fp32 (zeroed here): sum_dy | sum_dy_xhat  (== dbeta | dgamma).
-int b200dp_bn_bwd(const void* dy, const void* x, const void* y, void* dx, void* dres, const float* scale_a,
+// `relu_mask`: the byte-per-8-channels mask written by b200dp_bn_fwd (required when relu != 0).
+int b200dp_bn_bwd(const void* dy, const void* x, const void* relu_mask, void* dx, void* dres, const float* scale_a,
                   const float* mean, const float* invstd, float* sums, long long M, int C, int relu,
                   unsigned long long stream) {
   if (!shape_ok(C)) return -1;
@@ -444,9 +454,10 @@ int b200dp_bn_bwd(const void* dy, const void* x, const void* y, void* dx, void* 
   cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
   if (e != cudaSuccess) return fail("memset", e);
   const int grid = grid_for(nvec, V);
-  bn_bwd_reduce_kernel<<<grid, THREADS, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint4*)y, mean,
-                                                 invstd, sums, sums + C, nvec, V, relu);
-  bn_bwd_apply_kernel<<<grid, THREADS, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint4*)y,
+  bn_bwd_reduce_kernel<<<reduce_grid(), RTHREADS, 0, st>>>((const uint4*)dy, (const uint4*)x,
+                                                           (const uint8_t*)relu_mask, mean, sums, sums + C,
+                                                           nvec, V, relu);
+  bn_bwd_apply_kernel<<<grid, THREADS, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint8_t*)relu_mask,
                                                 (uint4*)dx, (uint4*)dres, mean, invstd, scale_a, sums,
                                                 sums + C, 1.0f / (float)M, nvec, V, relu);
   e = cudaGetLastError();

@@ -322,23 +322,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    // fused BN statistics: lane l owns column (chunk*32 + l) of the current n-block; partial sums
-    // stay in registers across all tiles of that n-block and are flushed with one atomic each.
-    float st_sum[BN / 32], st_sq[BN / 32];
-#pragma unroll
-    for (int i = 0; i < BN / 32; ++i) st_sum[i] = st_sq[i] = 0.f;
+    // fused BN statistics (opt-in): lane l owns column (chunk*32 + l) of the current n-block;
+    // per-warp partial sums live in shared memory across all tiles of that n-block and are
+    // flushed with one atomic per column.
+    __shared__ float st_acc[4][2][BN];
+    if (p.col_stats != nullptr) {
+      for (int i = lane; i < BN; i += 32) st_acc[q][0][i] = st_acc[q][1][i] = 0.f;
+      __syncwarp();
+    }
     int st_n_idx = -1;
     auto flush_stats = [&]() {
       if (p.col_stats == nullptr || st_n_idx < 0) return;
-#pragma unroll
-      for (int i = 0; i < BN / 32; ++i) {
-        const int col = st_n_idx + i * 32 + lane;
+      for (int i = lane; i < BN; i += 32) {
+        const int col = st_n_idx + i;
         if (col < p.N) {
-          atomicAdd(p.col_stats + col, st_sum[i]);
-          atomicAdd(p.col_stats + p.N + col, st_sq[i]);
+          atomicAdd(p.col_stats + col, st_acc[q][0][i]);
+          atomicAdd(p.col_stats + p.N + col, st_acc[q][1][i]);
         }
-        st_sum[i] = st_sq[i] = 0.f;
+        st_acc[q][0][i] = st_acc[q][1][i] = 0.f;
       }
+      __syncwarp();
     };
     for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
       const int tile = w % tiles, split = w / tiles;
@@ -354,7 +357,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       tc_fence_after();
       const int row = m_idx + q * 32 + lane;
       const bool row_ok = row < p.M;
-#pragma unroll
+#pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
@@ -384,8 +387,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               b2[i] = (up ? b2[i + half] : b2[i]) + rb;
             }
           }
-          st_sum[c0 / 32] += a[0];
-          st_sq[c0 / 32] += b2[0];
+          st_acc[q][0][c0 + lane] += a[0];
+          st_acc[q][1][c0 + lane] += b2[0];
         }
         if (!row_ok || col0 >= p.N || !has_k) continue;
         float v[32];

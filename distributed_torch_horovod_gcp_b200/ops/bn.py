@@ -23,7 +23,7 @@ def register(lib, have):
         return
     _lib = lib
     vp, i, f, ll, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_uint64
-    lib.b200dp_bn_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, i, i, i, u64]
+    lib.b200dp_bn_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, i, i, i, vp, u64]
     lib.b200dp_bn_apply.argtypes = [vp, vp, vp, vp, vp, ll, i, i, u64]
     lib.b200dp_bn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, i, u64]
     lib.b200dp_bn_supported.argtypes = [i]
@@ -65,6 +65,8 @@ class _BNActFn(torch.autograd.Function):
         if stats_in is not None:
             stats = stats_in              # accumulated by the producing GEMM's epilogue
         pbf16 = int(gamma.dtype == torch.bfloat16)
+        # ReLU sign bits, 1 byte per 8 channels: the backward reads 1/16th of what y would cost
+        mask = torch.empty(M * (C // 8), dtype=torch.uint8, device=dev) if relu else None
         st = torch.cuda.current_stream(dev).cuda_stream
         _ck(_lib.b200dp_bn_fwd(x.data_ptr(), residual.data_ptr() if residual is not None else None,
                                y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(),
@@ -72,15 +74,16 @@ class _BNActFn(torch.autograd.Function):
                                running_mean.data_ptr() if running_mean is not None else None,
                                running_var.data_ptr() if running_var is not None else None,
                                M, C, float(eps), float(momentum), int(relu), pbf16,
-                               int(stats_in is not None), st))
+                               int(stats_in is not None),
+                               mask.data_ptr() if mask is not None else None, st))
         counters.bump("bn_fwd", 2 if stats_in is not None else 3)
-        ctx.save_for_backward(x, y if relu else None, mean, invstd, a)
+        ctx.save_for_backward(x, mask, mean, invstd, a)
         ctx.relu, ctx.has_res, ctx.pdtype = relu, residual is not None, gamma.dtype
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, mean, invstd, a = ctx.saved_tensors
+        x, mask, mean, invstd, a = ctx.saved_tensors
         N, C, H, W = x.shape
         M = N * H * W
         if not dy.is_contiguous(memory_format=torch.channels_last):
@@ -90,13 +93,13 @@ class _BNActFn(torch.autograd.Function):
             else None
         sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
         st = torch.cuda.current_stream(x.device).cuda_stream
-        _ck(_lib.b200dp_bn_bwd(dy.data_ptr(), x.data_ptr(), y.data_ptr() if y is not None else None,
+        _ck(_lib.b200dp_bn_bwd(dy.data_ptr(), x.data_ptr(), mask.data_ptr() if mask is not None else None,
                                dx.data_ptr(), dres.data_ptr() if dres is not None else None,
                                a.data_ptr(), mean.data_ptr(), invstd.data_ptr(), sums.data_ptr(),
                                M, C, int(ctx.relu), st))
         counters.bump("bn_bwd", 2)
         dbeta = sums[:C].to(ctx.pdtype)
-        dgamma = sums[C:].to(ctx.pdtype)
+        dgamma = (sums[C:] * invstd).to(ctx.pdtype)      # kernel accumulates sum(dz * (x - mean))
         if ctx.has_res and dres is None:
             dres = dy                       # no ReLU: the residual branch gets dy unchanged
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None
@@ -124,7 +127,7 @@ def bn_act(x, bn: torch.nn.BatchNorm2d, relu: bool, residual: Optional[torch.Ten
     return y
 
 
-_FUSE_STATS = os.environ.get("B200DP_FUSE_BN_STATS", "1") == "1"
+_FUSE_STATS = os.environ.get("B200DP_FUSE_BN_STATS", "0") == "1"   # opt-in: epilogue cost > saved pass
 
 
 def _is_gemm_conv(x, conv) -> bool:

@@ -20,8 +20,8 @@ for row in r:
     v = float(row[vi].replace(",", ""))
     u = row[ui]
     ns = v * {"ns": 1, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6, "nsecond": 1, "second": 1e9}.get(u, 1)
-    name = re.sub(r"<.*", "", row[ki])
-    name = re.sub(r"\(.*", "", name)[:70]
+    name = row[ki].replace("(anonymous namespace)::", "").replace("void ", "")
+    name = re.sub(r"\(.*", "", name).replace("at::native::", "")[:90]
     tot[name] += ns
     cnt[name] += 1
 allns = sum(tot.values())
