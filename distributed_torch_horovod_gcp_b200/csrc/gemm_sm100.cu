@@ -41,8 +41,7 @@ struct GemmParams {
   const void* bias_f32;    // fp32 [N] or nullptr
   const void* residual;    // bf16 [M, ldc] or nullptr (added after act; or `aux` for act 3/4)
   void* preact;            // optional bf16 [M, ldc]: pre-activation values (saved for backward)
-  float* col_stats;        // optional fp32 [2*N]: += per-column sum | sum of squares of the bf16 output
-                           // (BatchNorm statistics fused into the producing GEMM; out_mode 0 only)
+  int tma_store;           // out_mode 0: stage the tile in swizzled smem and write it with TMA bulk stores
   float alpha;
 };
 
@@ -86,6 +85,18 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -192,20 +203,22 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BN;       // double-buffered fp32 accumulator
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STORE_BYTES = 4 * 2 * 4096;   // per epilogue warp: 2 x (32 rows x 128 B) staging
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* smem_store = smem + C::STAGES * C::STAGE_BYTES;   // 1024B-aligned staging for TMA stores
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_store + C::STORE_BYTES);
   uint64_t* full_bar = bars;                     // [STAGES]
   uint64_t* empty_bar = bars + C::STAGES;        // [STAGES]
   uint64_t* tmem_full = bars + 2 * C::STAGES;    // [2]
@@ -218,6 +231,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (p.tma_store) tma_prefetch_desc(&map_c);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -322,110 +336,61 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    // fused BN statistics (opt-in): lane l owns column (chunk*32 + l) of the current n-block;
-    // per-warp partial sums live in shared memory across all tiles of that n-block and are
-    // flushed with one atomic per column.
-    __shared__ float st_acc[4][2][BN];
-    if (p.col_stats != nullptr) {
-      for (int i = lane; i < BN; i += 32) st_acc[q][0][i] = st_acc[q][1][i] = 0.f;
-      __syncwarp();
-    }
-    int st_n_idx = -1;
-    auto flush_stats = [&]() {
-      if (p.col_stats == nullptr || st_n_idx < 0) return;
-      for (int i = lane; i < BN; i += 32) {
-        const int col = st_n_idx + i;
-        if (col < p.N) {
-          atomicAdd(p.col_stats + col, st_acc[q][0][i]);
-          atomicAdd(p.col_stats + p.N + col, st_acc[q][1][i]);
-        }
-        st_acc[q][0][i] = st_acc[q][1][i] = 0.f;
-      }
-      __syncwarp();
-    };
+    uint8_t* my_store = smem_store + q * (2 * 4096);
+    int store_buf = 0;
     for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
-      const int tile = w % tiles, split = w / tiles;
+      const int tile = w % tiles;
       const int m_idx = (tile % p.num_m_blocks) * BLOCK_M;
       const int n_idx = (tile / p.num_m_blocks) * BN;
-      if (n_idx != st_n_idx) {
-        flush_stats();
-        st_n_idx = n_idx;
-      }
-      const int kb0 = split * kb_per_split;
-      const bool has_k = min(kb0 + kb_per_split, p.num_k_blocks) > kb0;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int row = m_idx + q * 32 + lane;
       const bool row_ok = row < p.M;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        // two x32 loads in flight before the wait: 64 accumulator columns of this lane's row
+        uint32_t r[64];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
         tc_ld_32x32b_x32(taddr, r);
+        tc_ld_32x32b_x32(taddr + 32, r + 32);
         tc_wait_ld();
         const int col0 = n_idx + c0;
-        if (p.col_stats != nullptr && col0 < p.N) {
-          // warp-collective: every lane participates (rows >= M hold exact zeros: TMA zero-fill)
-          float a[32], b2[32];
+        if (col0 >= p.N) continue;                       // warp-uniform
+        const int ncols = min(64, p.N - col0);           // N % 8 == 0 is enforced by the host
+        float v[64];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = __bfloat162float(__float2bfloat16_rn(__uint_as_float(r[i]) * p.alpha));
-            a[i] = x;
-            b2[i] = x * x;
-          }
-          // butterfly reduce-scatter over the 32 lanes: after 5 steps lane l holds column l
-#pragma unroll
-          for (int half = 16; half >= 1; half >>= 1) {
-            const bool up = (lane & half) != 0;
-#pragma unroll
-            for (int i = 0; i < half; ++i) {
-              const float sa = up ? a[i] : a[i + half];
-              const float sb = up ? b2[i] : b2[i + half];
-              const float ra = __shfl_xor_sync(0xffffffffu, sa, half);
-              const float rb = __shfl_xor_sync(0xffffffffu, sb, half);
-              a[i] = (up ? a[i + half] : a[i]) + ra;
-              b2[i] = (up ? b2[i + half] : b2[i]) + rb;
-            }
-          }
-          st_acc[q][0][c0 + lane] += a[0];
-          st_acc[q][1][c0 + lane] += b2[0];
-        }
-        if (!row_ok || col0 >= p.N || !has_k) continue;
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-        const int ncols = min(32, p.N - col0);     // N % 8 == 0 is enforced by the host
-        if (p.out_mode == 0 || p.out_mode == 2) {
+        for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+        if (p.out_mode != 1 && row_ok) {
           if (p.bias != nullptr) {
             const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
+            for (int i = 0; i < 64; ++i)
               if (i < ncols) v[i] += __bfloat162float(b[i]);
           } else if (p.bias_f32 != nullptr) {
             const float* b = reinterpret_cast<const float*>(p.bias_f32) + col0;
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
+            for (int i = 0; i < 64; ++i)
               if (i < ncols) v[i] += b[i];
           }
           if (p.preact != nullptr) {
             uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.preact) +
                                                  (size_t)row * p.ldc + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 8; ++j)
               if (j * 8 < ncols) pp[j] = pack8(v + j * 8);
           }
           if (p.act == 1) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+            for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.0f);
           } else if (p.act == 2) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+            for (int i = 0; i < 64; ++i) v[i] = gelu_erf(v[i]);
           }
           if (p.residual != nullptr) {
             const uint4* rp = reinterpret_cast<const uint4*>(
                 reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldc + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
               if (j * 8 < ncols) {
                 float a[8];
                 unpack8(rp[j], a);
@@ -439,24 +404,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           }
         }
-        if (p.out_mode == 0) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) +
-                                                (size_t)row * p.ldc + col0);
+        if (p.out_mode == 0 && p.tma_store) {
+          // stage 32 rows x 128 B in the 128B-swizzled layout (conflict-free 16 B stores), then one
+          // lane issues a bulk tensor store; TMA clips rows >= M and columns >= N.
+          uint8_t* buf = my_store + store_buf * 4096;
+          if (lane == 0) tma_store_wait_read<1>();       // the store issued 2 chunks ago has read `buf`
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j * 8 < ncols) dst[j] = pack8(v + j * 8);
-        } else {
-          float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-          if (p.out_mode == 2) {
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8(v + j * 8);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_c, buf, col0, m_idx + q * 32);
+            tma_store_commit();
+          }
+          store_buf ^= 1;
+        } else if (row_ok) {
+          if (p.out_mode == 0) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) +
+                                                  (size_t)row * p.ldc + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (j * 4 < ncols)
-                reinterpret_cast<float4*>(dst)[j] =
-                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (j * 8 < ncols) dst[j] = pack8(v + j * 8);
           } else {
+            float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+            if (p.out_mode == 2) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncols) atomicAdd(dst + i, v[i]);     // RED.ADD.F32 (split-K accumulation)
+              for (int j = 0; j < 16; ++j)
+                if (j * 4 < ncols)
+                  reinterpret_cast<float4*>(dst)[j] =
+                      make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 64; ++i)
+                if (i < ncols) atomicAdd(dst + i, v[i]);     // RED.ADD.F32 (split-K accumulation)
+            }
           }
         }
       }
@@ -465,7 +448,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    flush_stats();
+    if (p.tma_store && lane == 0) tma_store_wait_all();   // smem must outlive the bulk reads
   }
 
   tc_fence_before();
@@ -506,6 +489,7 @@ int ensure_init() {
 }
 
 // 2D bf16 tensor map: `rows` x `cols` (cols contiguous), row pitch `ld` elements, box {64, box_rows}.
+// (the same encoding serves the loads of A/B and the 32-row bulk stores of C)
 int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 2};
@@ -519,7 +503,8 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint
 }
 
 template <int BN, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int max_ctas, cudaStream_t st) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmParams& p,
+           int max_ctas, cudaStream_t st) {
   using C = Cfg<BN>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
@@ -531,7 +516,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, in
   const int work = p.num_m_blocks * p.num_n_blocks * p.splits;
   int grid = work < g_num_sms ? work : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, p);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mc, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);
   return 0;
@@ -549,7 +534,7 @@ const char* b200dp_gemm_last_error() { return g_err; }
 // 16-byte aligned base pointers and leading dimensions.
 int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                      int a_mn, int b_mn, const void* bias_bf16, const void* bias_f32, const void* residual,
-                     void* preact, float* col_stats, int act, int out_mode, float alpha, int splits, int block_n, int max_ctas,
+                     void* preact, int act, int out_mode, float alpha, int splits, int block_n, int max_ctas,
                      unsigned long long stream) {
   if (ensure_init()) return -1;
   if (M <= 0 || N <= 0 || K <= 0) return fail("bad shape");
@@ -573,17 +558,22 @@ int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K,
   }
   p.act = act; p.out_mode = out_mode; p.C = C; p.bias = bias_bf16; p.bias_f32 = bias_f32;
   p.residual = residual; p.preact = preact; p.alpha = alpha;
-  p.col_stats = (out_mode == 0) ? col_stats : nullptr;
-  CUtensorMap ma, mb;
+  p.tma_store = (out_mode == 0) ? 1 : 0;
+  CUtensorMap ma, mb, mc;
   if (a_mn ? make_map(&ma, A, K, M, lda, BLOCK_K) : make_map(&ma, A, M, K, lda, BLOCK_M)) return -1;
   if (b_mn ? make_map(&mb, B, K, N, ldb, BLOCK_K) : make_map(&mb, B, N, K, ldb, BN)) return -1;
+  if (p.tma_store) {
+    if (make_map(&mc, C, M, N, ldc, 32)) return -1;
+  } else {
+    mc = ma;   // unused
+  }
   cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
 #define DISPATCH(BNV)                                                                         \
   if (BN == BNV) {                                                                            \
-    if (!a_mn && !b_mn) return launch<BNV, false, false>(ma, mb, p, max_ctas, st);            \
-    if (!a_mn && b_mn) return launch<BNV, false, true>(ma, mb, p, max_ctas, st);              \
-    if (a_mn && !b_mn) return launch<BNV, true, false>(ma, mb, p, max_ctas, st);              \
-    return launch<BNV, true, true>(ma, mb, p, max_ctas, st);                                  \
+    if (!a_mn && !b_mn) return launch<BNV, false, false>(ma, mb, mc, p, max_ctas, st);            \
+    if (!a_mn && b_mn) return launch<BNV, false, true>(ma, mb, mc, p, max_ctas, st);              \
+    if (a_mn && !b_mn) return launch<BNV, true, false>(ma, mb, mc, p, max_ctas, st);              \
+    return launch<BNV, true, true>(ma, mb, mc, p, max_ctas, st);                                  \
   }
   DISPATCH(64)
   DISPATCH(128)

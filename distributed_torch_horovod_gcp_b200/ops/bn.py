@@ -127,9 +127,6 @@ def bn_act(x, bn: torch.nn.BatchNorm2d, relu: bool, residual: Optional[torch.Ten
     return y
 
 
-_FUSE_STATS = os.environ.get("B200DP_FUSE_BN_STATS", "0") == "1"   # opt-in: epilogue cost > saved pass
-
-
 def _is_gemm_conv(x, conv) -> bool:
     w = conv.weight
     return (_USE_GEMM_1X1 and _gemm._lib is not None and conv.kernel_size == (1, 1)
@@ -138,28 +135,23 @@ def _is_gemm_conv(x, conv) -> bool:
             and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0)
 
 
-def conv2d(x, conv: torch.nn.Conv2d, col_stats: Optional[torch.Tensor] = None):
-    """Convolution of an NHWC bf16 activation; 1x1/stride-1 -> tcgen05 GEMM (optionally
-    accumulating the BatchNorm statistics of its output in the epilogue)."""
+def conv2d(x, conv: torch.nn.Conv2d):
+    """Convolution of an NHWC bf16 activation; 1x1/stride-1 -> tcgen05 GEMM."""
     w = conv.weight
     if _is_gemm_conv(x, conv):
         N, C, H, W = x.shape
         x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, C)             # view: NHWC rows
-        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C), col_stats=col_stats)   # [M, Cout]
+        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C))              # [M, Cout]
         return y2.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2)      # logical NCHW, NHWC memory
     return F.conv2d(x, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
 def conv_bn_act(x, conv, bn, relu: bool, residual=None):
-    Cout = conv.weight.shape[0]
-    fuse = (_FUSE_STATS and bn.training and bn.weight is not None and _is_gemm_conv(x, conv)
-            and bool(_lib.b200dp_bn_supported(Cout)))
-    stats = torch.zeros(2 * Cout, dtype=torch.float32, device=x.device) if fuse else None
-    y = conv2d(x, conv, stats)
+    y = conv2d(x, conv)
     C = y.shape[1]
     if bn_supported(y, C) and bn.weight is not None and \
             (residual is None or residual.dtype == torch.bfloat16):
-        return bn_act(y, bn, relu, residual, stats)
+        return bn_act(y, bn, relu, residual)
     y = bn(y)
     if residual is not None:
         y = y + residual

@@ -28,8 +28,8 @@ def register(lib, have):
         return
     _lib = lib
     vp, i, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
-    lib.b200dp_gemm_bf16.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, vp, i, i, f,
-                                     i, i, i, ctypes.c_uint64]
+    lib.b200dp_gemm_bf16.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, i, i, f, i,
+                                     i, i, ctypes.c_uint64]
     lib.b200dp_gemm_bf16.restype = i
     lib.b200dp_gemm_last_error.restype = ctypes.c_char_p
     have["gemm"] = True
@@ -39,7 +39,7 @@ def register(lib, have):
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K: int, *,
          a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, preact: Optional[torch.Tensor] = None,
-         col_stats: Optional[torch.Tensor] = None, act: int = 0, out_mode: int = 0, alpha: float = 1.0, splits: int = 1, block_n: int = 0,
+         act: int = 0, out_mode: int = 0, alpha: float = 1.0, splits: int = 1, block_n: int = 0,
          max_ctas: int = 0) -> torch.Tensor:
     """Raw kernel call.  ``a``: [M,K] (K-major) or [K,M] (MN-major) bf16 with contiguous rows;
     ``b``: [N,K] or [K,N]; ``out``: [M,N] bf16 (out_mode 0) or fp32 (1: atomic add, 2: store)."""
@@ -53,7 +53,6 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
         int(a_mn), int(b_mn), bias_bf, bias_f32,
         residual.data_ptr() if residual is not None else None,
         preact.data_ptr() if preact is not None else None,
-        col_stats.data_ptr() if col_stats is not None else None,
         act, out_mode, float(alpha), splits, block_n, max_ctas,
         torch.cuda.current_stream(a.device).cuda_stream)
     if rc != 0:
@@ -78,7 +77,7 @@ def _splits_for(M_out: int, N_out: int, K_red: int, sms: int = 148) -> int:
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, act, residual, col_stats=None):
+    def forward(ctx, x, weight, bias, act, residual):
         K = weight.shape[1]
         N = weight.shape[0]
         x2 = x.reshape(-1, K)
@@ -93,7 +92,7 @@ class _LinearFn(torch.autograd.Function):
             r2 = residual.reshape(-1, N)
             if not r2.is_contiguous():
                 r2 = r2.contiguous()
-        gemm(x2, weight, y, M, N, K, bias=bias, residual=r2, preact=z, act=act, col_stats=col_stats)
+        gemm(x2, weight, y, M, N, K, bias=bias, residual=r2, preact=z, act=act)
         ctx.save_for_backward(x2, weight, z)
         ctx.act, ctx.has_bias, ctx.has_res = act, bias is not None, residual is not None
         ctx.x_shape = x.shape
@@ -133,10 +132,8 @@ class _LinearFn(torch.autograd.Function):
             dw = acc.to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dz.float().sum(0).to(ctx.bias_dtype)
-        return dx, dw, db, None, dres, None
+        return dx, dw, db, None, dres
 
 
-def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, col_stats=None):
-    """``col_stats`` (fp32 [2N], zeroed by the caller) receives the per-column sum and sum of
-    squares of the output — BatchNorm statistics fused into the producing GEMM's epilogue."""
-    return _LinearFn.apply(x, weight, bias, ACT[act], residual, col_stats)
+def linear(x, weight, bias=None, act: Optional[str] = None, residual=None):
+    return _LinearFn.apply(x, weight, bias, ACT[act], residual)
