@@ -42,6 +42,9 @@ def parse():
     p.add_argument("--image-size", type=int, default=224)
     p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--graph", default=os.environ.get("BENCH_GRAPH", "auto"), choices=["auto", "on", "off"],
+                   help="capture the whole training step (fwd+bwd+fused allreduce/update) in one CUDA "
+                        "graph (ours only; 'auto' falls back to eager if capture fails)")
     p.add_argument("--lr", type=float, default=0.1)
     return p.parse_args()
 
@@ -140,13 +143,31 @@ def main():
     dev_batches = [data.next() for _ in range(2)]
     torch.cuda.synchronize()
 
-    def train_step(x, y):
+    def eager_step(x, y):
         out = step_model(x)
         loss = F.cross_entropy(out.float(), y)
         loss.backward()
         opt.step()
         opt.zero_grad(set_to_none=(args.impl != "ours"))
-        return loss
+        return loss.detach()
+
+    train_step, graphed = eager_step, False
+    if args.impl == "ours" and args.graph != "off" and getattr(opt, "fused_engine", None) is not None:
+        from distributed_torch_horovod_gcp_b200.utils.graph import GraphedStep
+        ok = True
+        try:
+            gs = GraphedStep(eager_step, list(dev_batches[0]), warmup=3)
+        except Exception as e:  # noqa: BLE001
+            ok = False
+            if args.graph == "on":
+                raise
+            print(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); running eager",
+                  file=sys.stderr)
+        if world > 1:      # all ranks must take the same path (graphs replay collectives)
+            votes = hvd.allgather_object(ok)
+            ok = all(votes)
+        if ok:
+            train_step, graphed = gs, True
 
     def sync_all():
         torch.cuda.synchronize()
@@ -178,6 +199,8 @@ def main():
     sync_all()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = our_launches() - l0
+    if graphed:
+        launches = gs.kernels_per_replay * args.steps      # replayed graph nodes, counted at capture
     final_loss = float(loss)
 
     # ---------------- end-to-end region through the public API (H2D inputs + D2H loss per step)
@@ -221,7 +244,7 @@ def main():
             "config": {"model": args.model, "global_batch": args.batch * world,
                        "per_gpu_batch": args.batch, "image_size": args.image_size,
                        "parallelism": f"dp{world}", "optimizer": "SGD momentum=0.9 wd=1e-4",
-                       "layout": "NHWC bf16",
+                       "layout": "NHWC bf16", "cuda_graph": graphed,
                        "l2": "no explicit flush: per-step working set (activations, several GB) "
                              ">> 126 MB L2",
                        "comm": (opt.fused_engine.algorithms() if args.impl == "ours" and

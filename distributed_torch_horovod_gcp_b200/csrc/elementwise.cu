@@ -362,6 +362,49 @@ __global__ void __launch_bounds__(THREADS) maxpool_bwd_kernel(const uint4* __res
   }
 }
 
+// ---- stem im2col: 7x7 / stride 2 / pad 3 over NHWC bf16 with C = 3 ------------------------------------
+// Turns the ResNet stem into a plain GEMM for the tcgen05 kernel: A[m][k], m = (n, oh, ow),
+// k = (kh*7 + kw)*3 + c, row pitch KP = 152 (147 taps + 5 zero columns so rows are 16-byte multiples).
+// One block per output row (n, oh): the 7 input rows it needs are staged in shared memory with
+// coalesced 128-bit loads, then every thread assembles 8-element output vectors.
+constexpr int STEM_KP = 152;
+__global__ void __launch_bounds__(THREADS) stem_im2col_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              uint4* __restrict__ out, int H, int W,
+                                                              int OH, int OW) {
+  extern __shared__ __align__(16) __nv_bfloat16 rows[];     // [7][W*3]
+  const int n = blockIdx.x / OH, oh = blockIdx.x % OH;
+  const int row_elems = W * 3;
+  const int vec_per_row = row_elems / 8;                     // W*3*2 bytes is a multiple of 16 for W % 8 == 0
+  for (int i = threadIdx.x; i < 7 * vec_per_row; i += THREADS) {
+    const int r = i / vec_per_row, v = i % vec_per_row;
+    const int ih = oh * 2 - 3 + r;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (ih >= 0 && ih < H)
+      val = reinterpret_cast<const uint4*>(x + ((size_t)n * H + ih) * row_elems)[v];
+    reinterpret_cast<uint4*>(rows + r * row_elems)[v] = val;
+  }
+  __syncthreads();
+  constexpr int VPR = STEM_KP / 8;                           // 19 vectors per output row
+  uint4* dst = out + ((size_t)n * OH + oh) * OW * VPR;
+  const __nv_bfloat16 zero = __float2bfloat16(0.f);
+  for (int i = threadIdx.x; i < OW * VPR; i += THREADS) {
+    const int ow = i / VPR, j = i % VPR;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = j * 8 + e;
+      __nv_bfloat16 val = zero;
+      if (k < 147) {
+        const int kh = k / 21, rem = k % 21;                 // rem = kw*3 + c
+        const int iw = ow * 2 - 3 + rem / 3;
+        if (iw >= 0 && iw < W) val = rows[kh * row_elems + (ow * 2 - 3) * 3 + rem];
+      }
+      v[e] = val;
+    }
+    dst[i] = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
 thread_local char g_err[256];
 int fail(const char* what, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -491,6 +534,18 @@ int b200dp_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, 
                                                                              (uint4*)dx, N, H, W, OH, OW, V);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("maxpool_bwd launch", e);
+  return 0;
+}
+
+// x: NHWC bf16 [N,H,W,3] (H, W multiples of 8); out: [N*OH*OW, 152] bf16, OH = H/2, OW = W/2.
+int b200dp_stem_im2col(const void* x, void* out, int N, int H, int W, unsigned long long stream) {
+  if ((W % 8) || (H % 2)) return -1;
+  const int OH = H / 2, OW = W / 2;
+  const size_t smem = (size_t)7 * W * 3 * sizeof(__nv_bfloat16);
+  stem_im2col_kernel<<<N * OH, THREADS, smem, (cudaStream_t)(uintptr_t)stream>>>(
+      (const __nv_bfloat16*)x, (uint4*)out, H, W, OH, OW);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("stem_im2col launch", e);
   return 0;
 }
 

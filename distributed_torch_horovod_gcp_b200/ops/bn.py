@@ -30,6 +30,9 @@ def register(lib, have):
     lib.b200dp_ew_last_error.restype = ctypes.c_char_p
     have["bn_act"] = True
     have["conv_bn_act"] = True
+    if hasattr(lib, "b200dp_stem_im2col"):
+        lib.b200dp_stem_im2col.argtypes = [vp, vp, i, i, i, u64]
+        have["stem_conv"] = True
     if hasattr(lib, "b200dp_maxpool_fwd"):
         lib.b200dp_maxpool_fwd.argtypes = [vp, vp, vp, i, i, i, i, u64]
         lib.b200dp_maxpool_bwd.argtypes = [vp, vp, vp, i, i, i, i, u64]
@@ -135,14 +138,67 @@ def _is_gemm_conv(x, conv) -> bool:
             and w.shape[0] % 8 == 0 and w.shape[1] % 8 == 0)
 
 
+_USE_STEM_GEMM = os.environ.get("B200DP_STEM_GEMM", "1") == "1"
+STEM_KP = 152
+
+
+class _StemConvFn(torch.autograd.Function):
+    """ResNet stem (7x7, stride 2, pad 3, 3 input channels) as im2col + tcgen05 GEMM.  cuDNN runs
+    this layer on legacy sm80 kernels (1.5 ms fwd + 0.8 ms wgrad at batch 256); the im2col matrix
+    ([N*112*112, 152] bf16) is kept for the weight gradient — HBM capacity is not the constraint
+    on a 180 GB part, bandwidth is."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        N, C, H, W = x.shape
+        OH, OW = H // 2, W // 2
+        M = N * OH * OW
+        cols = torch.empty((M, STEM_KP), dtype=torch.bfloat16, device=x.device)
+        _ck(_lib.b200dp_stem_im2col(x.data_ptr(), cols.data_ptr(), N, H, W,
+                                    torch.cuda.current_stream(x.device).cuda_stream))
+        counters.bump("stem_im2col")
+        Cout = weight.shape[0]
+        wp = torch.zeros((Cout, STEM_KP), dtype=torch.bfloat16, device=x.device)
+        wp[:, :147] = weight.permute(0, 2, 3, 1).reshape(Cout, 147)      # [Cout][kh][kw][c]
+        y = torch.empty((M, Cout), dtype=torch.bfloat16, device=x.device)
+        _gemm.gemm(cols, wp, y, M, Cout, STEM_KP)
+        ctx.save_for_backward(cols)
+        ctx.wshape = weight.shape
+        return y.view(N, OH, OW, Cout).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (cols,) = ctx.saved_tensors
+        Cout = ctx.wshape[0]
+        M = cols.shape[0]
+        dy2 = dy.permute(0, 2, 3, 1).reshape(M, Cout)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        acc = torch.zeros((Cout, STEM_KP), dtype=torch.float32, device=dy.device)
+        _gemm.gemm(dy2, cols, acc, Cout, STEM_KP, M, a_mn=True, b_mn=True, out_mode=1,
+                   splits=_gemm._splits_for(Cout, STEM_KP, M))
+        dw = acc[:, :147].reshape(Cout, 7, 7, 3).permute(0, 3, 1, 2).to(torch.bfloat16)
+        return None, dw.contiguous(memory_format=torch.channels_last)
+
+
+def _is_stem_conv(x, conv) -> bool:
+    return (_USE_STEM_GEMM and _gemm._lib is not None and hasattr(_lib, "b200dp_stem_im2col")
+            and conv.kernel_size == (7, 7) and conv.stride == (2, 2) and conv.padding == (3, 3)
+            and conv.groups == 1 and conv.bias is None and conv.in_channels == 3
+            and conv.weight.dtype == torch.bfloat16 and _nhwc_ok(x) and not x.requires_grad
+            and x.shape[2] % 2 == 0 and x.shape[3] % 8 == 0 and conv.out_channels % 8 == 0)
+
+
 def conv2d(x, conv: torch.nn.Conv2d):
-    """Convolution of an NHWC bf16 activation; 1x1/stride-1 -> tcgen05 GEMM."""
+    """Convolution of an NHWC bf16 activation; 1x1/stride-1 and the 7x7 stem -> tcgen05 GEMM."""
     w = conv.weight
     if _is_gemm_conv(x, conv):
         N, C, H, W = x.shape
         x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, C)             # view: NHWC rows
         y2 = _gemm.linear(x2, w.reshape(w.shape[0], C))              # [M, Cout]
         return y2.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2)      # logical NCHW, NHWC memory
+    if _is_stem_conv(x, conv):
+        return _StemConvFn.apply(x, w)
     return F.conv2d(x, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 

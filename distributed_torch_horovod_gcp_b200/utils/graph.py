@@ -28,9 +28,14 @@ class GraphedStep:
                 fn(*self.static_in)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from ..ops import counters
+        from ..parallel.fused_engine import live_engines
+        count = lambda: counters.total() + sum(e.kernel_launches for e in live_engines())
+        c0 = count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_out = fn(*self.static_in)
+        self.kernels_per_replay = count() - c0     # hand-written kernels captured in the graph
         self.replays = 0
 
     def __call__(self, *inputs: torch.Tensor):

@@ -187,3 +187,22 @@ def test_maxpool_matches_torch():
         yr.backward(g.float())
         # ties are measure-zero for random inputs; bf16 accumulation of <= 4 terms
         assert _rel(x.grad, xr.grad) < 1e-2
+
+
+def test_stem_conv_matches_cudnn():
+    from distributed_torch_horovod_gcp_b200.ops import kernels, bn as B
+    assert kernels.has("stem_conv")
+    torch.manual_seed(8)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3, bias=False).cuda().to(torch.bfloat16).to(
+        memory_format=torch.channels_last)
+    x = torch.randn(4, 3, 64, 96, device="cuda").to(torch.bfloat16).contiguous(
+        memory_format=torch.channels_last)
+    assert B._is_stem_conv(x, conv)
+    y = B.conv2d(x, conv)
+    ref = torch.nn.functional.conv2d(x.float(), conv.weight.float(), None, 2, 3)
+    assert y.shape == ref.shape and _rel(y, ref) < 6e-3
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    wr = conv.weight.detach().float().requires_grad_(True)
+    torch.nn.functional.conv2d(x.float(), wr, None, 2, 3).backward(gy.float())
+    assert _rel(conv.weight.grad, wr.grad) < 1e-2
