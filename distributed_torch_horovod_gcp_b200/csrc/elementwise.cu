@@ -240,10 +240,17 @@ __global__ void __launch_bounds__(THREADS, 4) bn_bwd_apply_kernel(
     const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint8_t* __restrict__ mask, uint4* dx,
     uint4* dres, const float* __restrict__ mean, const float* __restrict__ invstd,
     const float* __restrict__ scale_a, const float* __restrict__ sum_dy,
-    const float* __restrict__ sum_dy_xhat, float inv_count, long long nvec, int V, int relu) {
+    const float* __restrict__ sum_dy_xhat, float inv_count, long long nvec, int V, int relu,
+    void* dgamma, void* dbeta, int pbf16) {
   constexpr int U = 2;
   const long long stride = (long long)gridDim.x * THREADS;
   const long long i0 = (long long)blockIdx.x * THREADS + threadIdx.x;
+  if (blockIdx.x == 0 && dgamma != nullptr) {     // parameter gradients, written in the param dtype
+    for (int c = threadIdx.x; c < V * 8; c += THREADS) {
+      st_param(dbeta, c, pbf16, sum_dy[c]);
+      st_param(dgamma, c, pbf16, sum_dy_xhat[c] * invstd[c]);
+    }
+  }
   if (i0 >= nvec) return;
   const int cg = (int)(i0 % V);
   float mv[8], iv[8], k1[8], k2[8], sc[8];
@@ -488,8 +495,8 @@ int b200dp_bn_apply(const void* x, const void* res, void* y, const float* a, con
 // sums: [2*C] fp32 (zeroed here): sum_dy | sum_dy_xhat  (== dbeta | dgamma).
 // `relu_mask`: the byte-per-8-channels mask written by b200dp_bn_fwd (required when relu != 0).
 int b200dp_bn_bwd(const void* dy, const void* x, const void* relu_mask, void* dx, void* dres, const float* scale_a,
-                  const float* mean, const float* invstd, float* sums, long long M, int C, int relu,
-                  unsigned long long stream) {
+                  const float* mean, const float* invstd, float* sums, void* dgamma, void* dbeta,
+                  int param_bf16, long long M, int C, int relu, unsigned long long stream) {
   if (!shape_ok(C)) return -1;
   cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
   const int V = C / 8;
@@ -502,7 +509,8 @@ int b200dp_bn_bwd(const void* dy, const void* x, const void* relu_mask, void* dx
                                                            nvec, V, relu);
   bn_bwd_apply_kernel<<<grid, THREADS, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint8_t*)relu_mask,
                                                 (uint4*)dx, (uint4*)dres, mean, invstd, scale_a, sums,
-                                                sums + C, 1.0f / (float)M, nvec, V, relu);
+                                                sums + C, 1.0f / (float)M, nvec, V, relu, dgamma, dbeta,
+                                                param_bf16);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail("bn_bwd launch", e);
   return 0;

@@ -33,8 +33,7 @@ class EncoderBlock(nn.Module):
         a = F2.attention(qkv, self.heads)                                  # [B,S,D]
         x = F2.linear(a, self.proj.weight, self.proj.bias, residual=x)
         h = F2.layer_norm(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps)
-        h = F2.linear(h, self.fc1.weight, self.fc1.bias, act="gelu")
-        return F2.linear(h, self.fc2.weight, self.fc2.bias, residual=x)
+        return F2.mlp(h, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, residual=x)
 
 
 class VisionTransformer(nn.Module):

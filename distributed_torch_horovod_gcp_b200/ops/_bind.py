@@ -6,7 +6,7 @@ from typing import Dict
 
 from . import gemm as _gemm
 from . import bn as _bn
-from .gemm import linear  # noqa: F401  (re-exported as kernels.linear)
+from .gemm import linear, mlp  # noqa: F401  (re-exported as kernels.linear / kernels.mlp)
 from .bn import conv_bn_act, bn_act, max_pool_3x3_s2  # noqa: F401
 
 

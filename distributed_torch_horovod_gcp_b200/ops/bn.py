@@ -25,7 +25,7 @@ def register(lib, have):
     vp, i, f, ll, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_uint64
     lib.b200dp_bn_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, i, i, i, vp, u64]
     lib.b200dp_bn_apply.argtypes = [vp, vp, vp, vp, vp, ll, i, i, u64]
-    lib.b200dp_bn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, i, u64]
+    lib.b200dp_bn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, ll, i, i, u64]
     lib.b200dp_bn_supported.argtypes = [i]
     lib.b200dp_ew_last_error.restype = ctypes.c_char_p
     have["bn_act"] = True
@@ -95,14 +95,15 @@ class _BNActFn(torch.autograd.Function):
         dres = torch.empty_like(x, memory_format=torch.channels_last) if (ctx.has_res and ctx.relu) \
             else None
         sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
+        dgb = torch.empty(2 * C, dtype=ctx.pdtype, device=x.device)
         st = torch.cuda.current_stream(x.device).cuda_stream
         _ck(_lib.b200dp_bn_bwd(dy.data_ptr(), x.data_ptr(), mask.data_ptr() if mask is not None else None,
                                dx.data_ptr(), dres.data_ptr() if dres is not None else None,
                                a.data_ptr(), mean.data_ptr(), invstd.data_ptr(), sums.data_ptr(),
-                               M, C, int(ctx.relu), st))
+                               dgb.data_ptr(), dgb.data_ptr() + C * dgb.element_size(),
+                               int(ctx.pdtype == torch.bfloat16), M, C, int(ctx.relu), st))
         counters.bump("bn_bwd", 2)
-        dbeta = sums[:C].to(ctx.pdtype)
-        dgamma = (sums[C:] * invstd).to(ctx.pdtype)      # kernel accumulates sum(dz * (x - mean))
+        dgamma, dbeta = dgb[:C], dgb[C:]                  # written by the kernel in the param dtype
         if ctx.has_res and dres is None:
             dres = dy                       # no ReLU: the residual branch gets dy unchanged
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None

@@ -73,6 +73,15 @@ def linear(x, weight, bias=None, act: Optional[str] = None, residual=None):
     return linear_reference(x, weight, bias, act, residual)
 
 
+def mlp(x, w1, b1, w2, b2, residual=None):
+    """Transformer MLP: fc2(gelu(fc1(x))) + residual (one fused autograd node on the kernel path)."""
+    k = _kernels(x)
+    if k is not None and k.has("linear") and k.linear_supported(x, w1) and b1 is not None \
+            and b2 is not None and w2.shape[0] % 8 == 0:
+        return k.mlp(x, w1, b1, w2, b2, residual)
+    return linear_reference(linear_reference(x, w1, b1, act="gelu"), w2, b2, residual=residual)
+
+
 # ------------------------------------------------------------------ layer norm
 def layer_norm(x, weight, bias, eps: float = 1e-6):
     k = _kernels(x)

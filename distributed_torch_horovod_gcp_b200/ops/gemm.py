@@ -70,9 +70,44 @@ def supported(x: torch.Tensor, weight: torch.Tensor) -> bool:
 
 def _splits_for(M_out: int, N_out: int, K_red: int, sms: int = 148) -> int:
     tiles = ((M_out + 127) // 128) * ((N_out + 127) // 128)
+    if tiles >= (2 * sms) // 3:
+        return 1                       # enough tiles to fill the GPU: no split, direct bf16 store
     kb = (K_red + 63) // 64
     want = max(1, (2 * sms) // max(tiles, 1))
     return max(1, min(want, kb // 4 if kb >= 8 else 1))
+
+
+_ones_cache = {}
+
+
+def _ones(M: int, device) -> torch.Tensor:
+    key = (M, str(device))
+    t = _ones_cache.get(key)
+    if t is None:
+        t = torch.ones((M, 8), dtype=torch.bfloat16, device=device)
+        _ones_cache[key] = t
+    return t
+
+
+def wgrad(dz: torch.Tensor, x2: torch.Tensor, N: int, K: int, M: int, dtype) -> torch.Tensor:
+    """dW[N,K] = dz[M,N]^T @ x2[M,K] with both operands MN-major (no transposes)."""
+    splits = _splits_for(N, K, M)
+    if splits == 1 and dtype == torch.bfloat16:
+        dw = torch.empty((N, K), dtype=torch.bfloat16, device=dz.device)
+        gemm(dz, x2, dw, N, K, M, a_mn=True, b_mn=True)              # TMA-store epilogue, bf16
+        return dw
+    acc = torch.zeros((N, K), dtype=torch.float32, device=dz.device)
+    gemm(dz, x2, acc, N, K, M, a_mn=True, b_mn=True, out_mode=1, splits=splits)
+    return acc.to(dtype)
+
+
+def bias_grad(dz: torch.Tensor, N: int, M: int, dtype) -> torch.Tensor:
+    """db[N] = column sums of dz — as a GEMM against a ones matrix (reads dz once, in bf16)."""
+    acc = torch.zeros((N, 8), dtype=torch.float32, device=dz.device)
+    kb = (M + 63) // 64
+    gemm(dz, _ones(M, dz.device), acc, N, 8, M, a_mn=True, b_mn=True, out_mode=1,
+         splits=max(1, min(kb // 4, (2 * 148) // max((N + 127) // 128, 1))), block_n=64)
+    return acc[:, 0].to(dtype)
 
 
 class _LinearFn(torch.autograd.Function):
@@ -109,15 +144,7 @@ class _LinearFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         dres = dy2.view(*ctx.x_shape[:-1], N) if ctx.has_res else None
         if ctx.act != 0:
-            # dz = dy * act'(z): elementwise epilogue of an identity-free pass is not worth a GEMM;
-            # use the fused torch op (memory-bound) — fused variants live in the dgrad epilogue.
-            if ctx.act == 1:
-                dz = dy2 * (z > 0).to(dy2.dtype)
-            else:
-                zf = z.float()
-                cdf = 0.5 * (1.0 + torch.erf(zf * 0.7071067811865476))
-                pdf = 0.3989422804014327 * torch.exp(-0.5 * zf * zf)
-                dz = (dy2.float() * (cdf + zf * pdf)).to(torch.bfloat16)
+            dz = act_backward(dy2, z, ctx.act)
         else:
             dz = dy2
         dx = dw = db = None
@@ -126,13 +153,70 @@ class _LinearFn(torch.autograd.Function):
             gemm(dz, weight, dx, M, K, N, b_mn=True)                       # dx = dz @ W
             dx = dx.view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            acc = torch.zeros((N, K), dtype=torch.float32, device=dy.device)
-            gemm(dz, x2, acc, N, K, M, a_mn=True, b_mn=True, out_mode=1,
-                 splits=_splits_for(N, K, M))                              # dW = dz^T @ x
-            dw = acc.to(weight.dtype)
+            dw = wgrad(dz, x2, N, K, M, weight.dtype)                      # dW = dz^T @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dz.float().sum(0).to(ctx.bias_dtype)
+            db = bias_grad(dz, N, M, ctx.bias_dtype)
         return dx, dw, db, None, dres
+
+
+def act_backward(dy2: torch.Tensor, z: torch.Tensor, act: int) -> torch.Tensor:
+    """dz = dy * act'(z) (stand-alone form; the MLP block fuses this into the fc2 dgrad epilogue)."""
+    if act == 1:
+        return dy2 * (z > 0).to(dy2.dtype)
+    zf = z.float()
+    cdf = 0.5 * (1.0 + torch.erf(zf * 0.7071067811865476))
+    pdf = 0.3989422804014327 * torch.exp(-0.5 * zf * zf)
+    return (dy2.float() * (cdf + zf * pdf)).to(torch.bfloat16)
+
+
+class _MLPFn(torch.autograd.Function):
+    """Transformer MLP block  out = fc2(gelu(fc1(x))) + residual  as ONE autograd node so the
+    backward can fuse  dz = (dy @ W2) * gelu'(z)  into the fc2-dgrad GEMM epilogue (act mode 3)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual):
+        D, Hd = w1.shape[1], w1.shape[0]
+        x2 = x.reshape(-1, D)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        dev = x.device
+        z = torch.empty((M, Hd), dtype=torch.bfloat16, device=dev)
+        h = torch.empty((M, Hd), dtype=torch.bfloat16, device=dev)
+        gemm(x2, w1, h, M, Hd, D, bias=b1, preact=z, act=2)
+        out = torch.empty((M, w2.shape[0]), dtype=torch.bfloat16, device=dev)
+        r2 = residual.reshape(M, -1) if residual is not None else None
+        if r2 is not None and not r2.is_contiguous():
+            r2 = r2.contiguous()
+        gemm(h, w2, out, M, w2.shape[0], Hd, bias=b2, residual=r2)
+        ctx.save_for_backward(x2, w1, w2, z, h)
+        ctx.x_shape, ctx.has_res = x.shape, residual is not None
+        ctx.bdt = (b1.dtype, b2.dtype)
+        return out.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w1, w2, z, h = ctx.saved_tensors
+        M, D = x2.shape
+        Hd, Do = w1.shape[0], w2.shape[0]
+        dy2 = dy.reshape(M, Do)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dev = dy.device
+        dz = torch.empty((M, Hd), dtype=torch.bfloat16, device=dev)
+        gemm(dy2, w2, dz, M, Hd, Do, b_mn=True, residual=z, act=3)        # (dy @ W2) * gelu'(z)
+        dw2 = wgrad(dy2, h, Do, Hd, M, w2.dtype)
+        db2 = bias_grad(dy2, Do, M, ctx.bdt[1])
+        dw1 = wgrad(dz, x2, Hd, D, M, w1.dtype)
+        db1 = bias_grad(dz, Hd, M, ctx.bdt[0])
+        dx = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+        gemm(dz, w1, dx, M, D, Hd, b_mn=True)
+        dres = dy2.view(*ctx.x_shape[:-1], Do) if ctx.has_res else None
+        return dx.view(ctx.x_shape), dw1, db1, dw2, db2, dres
+
+
+def mlp(x, w1, b1, w2, b2, residual=None):
+    return _MLPFn.apply(x, w1, b1, w2, b2, residual)
 
 
 def linear(x, weight, bias=None, act: Optional[str] = None, residual=None):

@@ -206,3 +206,24 @@ def test_stem_conv_matches_cudnn():
     wr = conv.weight.detach().float().requires_grad_(True)
     torch.nn.functional.conv2d(x.float(), wr, None, 2, 3).backward(gy.float())
     assert _rel(conv.weight.grad, wr.grad) < 1e-2
+
+
+def test_mlp_block_matches_torch():
+    from distributed_torch_horovod_gcp_b200.ops import functional as F2
+    torch.manual_seed(9)
+    x = (torch.randn(2, 197, 768, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    w1 = (torch.randn(3072, 768, device="cuda") * 0.03).to(torch.bfloat16).requires_grad_(True)
+    b1 = (torch.randn(3072, device="cuda") * 0.1).to(torch.bfloat16).requires_grad_(True)
+    w2 = (torch.randn(768, 3072, device="cuda") * 0.02).to(torch.bfloat16).requires_grad_(True)
+    b2 = (torch.randn(768, device="cuda") * 0.1).to(torch.bfloat16).requires_grad_(True)
+    ts = (x, w1, b1, w2, b2)
+    rs = [t.detach().float().requires_grad_(True) for t in ts]
+    y = F2.mlp(x, w1, b1, w2, b2, residual=x)
+    yr = torch.nn.functional.linear(torch.nn.functional.gelu(torch.nn.functional.linear(rs[0], rs[1], rs[2])),
+                                    rs[3], rs[4]) + rs[0]
+    assert _rel(y, yr) < 1e-2
+    g = torch.randn_like(y)
+    y.backward(g)
+    yr.backward(g.float())
+    for t, r, name in zip(ts, rs, "x w1 b1 w2 b2".split()):
+        assert _rel(t.grad, r.grad) < 3e-2, name
