@@ -94,7 +94,7 @@ class LSTM(nn.Module):
     def _use_fused(self, x: torch.Tensor) -> bool:
         if self._fused is False or not x.is_cuda:
             return False
-        if self.n_layers != 1 or self.directions != 1:
+        if self.directions != 1:
             return False
         from ..ops import lstm_fused
         return lstm_fused.available(self, x)

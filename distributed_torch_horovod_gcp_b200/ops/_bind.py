@@ -6,6 +6,9 @@ from typing import Dict
 
 from . import gemm as _gemm
 from . import bn as _bn
+from . import lstm_fused as _lstm
+from . import ln as _ln
+from .ln import layer_norm  # noqa: F401
 from .gemm import linear, mlp  # noqa: F401  (re-exported as kernels.linear / kernels.mlp)
 from .bn import conv_bn_act, bn_act, max_pool_3x3_s2  # noqa: F401
 
@@ -13,7 +16,13 @@ from .bn import conv_bn_act, bn_act, max_pool_3x3_s2  # noqa: F401
 def register(lib, have: Dict[str, bool]) -> None:
     _gemm.register(lib, have)
     _bn.register(lib, have)
+    _lstm.register(lib, have)
+    _ln.register(lib, have)
 
 
 def linear_supported(x, weight) -> bool:
     return _gemm.supported(x, weight)
+
+
+def layer_norm_supported(x, weight) -> bool:
+    return _ln.supported(x, weight)

@@ -227,3 +227,23 @@ def test_mlp_block_matches_torch():
     yr.backward(g.float())
     for t, r, name in zip(ts, rs, "x w1 b1 w2 b2".split()):
         assert _rel(t.grad, r.grad) < 3e-2, name
+
+
+@pytest.mark.parametrize("R,C", [(25216, 768), (128, 768), (1000, 1024), (33, 256)])
+def test_layer_norm_matches_torch(R, C):
+    from distributed_torch_horovod_gcp_b200.ops import kernels
+    assert kernels.has("layer_norm")
+    torch.manual_seed(10)
+    x = (torch.randn(R, C, device="cuda") * 2 + 0.5).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.rand(C, device="cuda") + 0.5).to(torch.bfloat16).requires_grad_(True)
+    b = (torch.randn(C, device="cuda") * 0.1).to(torch.bfloat16).requires_grad_(True)
+    xr, wr, br = [t.detach().float().requires_grad_(True) for t in (x, w, b)]
+    y = kernels.layer_norm(x, w, b, 1e-6)
+    yr = torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-6)
+    assert _rel(y, yr) < 1e-2
+    g = torch.randn_like(y)
+    y.backward(g)
+    yr.backward(g.float())
+    assert _rel(x.grad, xr.grad) < 2e-2
+    assert _rel(w.grad, wr.grad) < 2e-2
+    assert _rel(b.grad, br.grad) < 2e-2

@@ -81,3 +81,26 @@ def test_app_script_cuda_single(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     assert "this process is using device - cuda:0" in r.stdout
     assert r.stdout.count("train_loss") == 2 and "total training time in minutes" in r.stdout
+
+
+def test_lstm_fused_head_matches_torch():
+    """K6: fused last-step gather + 3 chained linears (fp32) vs the PyTorch composition."""
+    import copy
+    from distributed_torch_horovod_gcp_b200.models import LSTM
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    m = LSTM(23, 10, 1, 256, device=dev)
+    ref = copy.deepcopy(m)
+    ref._fused = False
+    x = torch.randn(32, 10, 23, device=dev)
+    y = torch.randn(32, 1, 1, device=dev)
+    assert m._use_fused(x), "fused head kernels not available"
+    torch.manual_seed(1)
+    out = m(x)
+    torch.manual_seed(1)
+    out_ref = ref(x)
+    torch.testing.assert_close(out, out_ref, rtol=1e-4, atol=1e-5)
+    F.mse_loss(out, y).backward()
+    F.mse_loss(out_ref, y).backward()
+    for (n, a), (_, b) in zip(m.named_parameters(), ref.named_parameters()):
+        torch.testing.assert_close(a.grad, b.grad, rtol=2e-3, atol=1e-5, msg=lambda s: f"{n}: {s}")
