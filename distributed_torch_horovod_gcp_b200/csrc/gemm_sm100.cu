@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace {
 
@@ -207,6 +208,114 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// Epilogue of one 32-row slab (this warp's TMEM lane quarter) of a 128 x BN accumulator: TMEM ->
+// registers -> alpha/bias/activation/residual -> bf16 via swizzled smem + TMA bulk store, or fp32
+// store / atomic add.  Shared by the 1-CTA and the 2-CTA (cta_group::2) kernels.
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtensorMap* map_c, uint32_t tmem_base,
+                                              int acc, int q, int lane, int m_row0, int n_idx,
+                                              uint8_t* my_store, int& store_buf) {
+  const int row = m_row0 + lane;
+  const bool row_ok = row < p.M;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 64) {
+    // two x32 loads in flight before the wait: 64 accumulator columns of this lane's row
+    uint32_t r[64];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+    tc_ld_32x32b_x32(taddr, r);
+    tc_ld_32x32b_x32(taddr + 32, r + 32);
+    tc_wait_ld();
+    const int col0 = n_idx + c0;
+    if (col0 >= p.N) continue;                       // warp-uniform
+    const int ncols = min(64, p.N - col0);           // N % 8 == 0 is enforced by the host
+    float v[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+    if (p.out_mode != 1 && row_ok) {
+      if (p.bias != nullptr) {
+        const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i < ncols) v[i] += __bfloat162float(b[i]);
+      } else if (p.bias_f32 != nullptr) {
+        const float* b = reinterpret_cast<const float*>(p.bias_f32) + col0;
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i < ncols) v[i] += b[i];
+      }
+      if (p.preact != nullptr) {
+        uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.preact) +
+                                             (size_t)row * p.ldc + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j * 8 < ncols) pp[j] = pack8(v + j * 8);
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.0f);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = gelu_erf(v[i]);
+      }
+      if (p.residual != nullptr) {
+        const uint4* rp = reinterpret_cast<const uint4*>(
+            reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldc + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j * 8 < ncols) {
+            float a[8];
+            unpack8(rp[j], a);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              if (p.act == 3) v[j * 8 + t] *= gelu_erf_grad(a[t]);
+              else if (p.act == 4) v[j * 8 + t] = a[t] > 0.0f ? v[j * 8 + t] : 0.0f;
+              else v[j * 8 + t] += a[t];
+            }
+          }
+        }
+      }
+    }
+    if (p.out_mode == 0 && p.tma_store) {
+      // stage 32 rows x 128 B in the 128B-swizzled layout (conflict-free 16 B stores), then one
+      // lane issues a bulk tensor store; TMA clips rows >= M and columns >= N.
+      uint8_t* buf = my_store + store_buf * 4096;
+      if (lane == 0) tma_store_wait_read<1>();       // the store issued 2 chunks ago has read `buf`
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8(v + j * 8);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(map_c, buf, col0, m_row0);
+        tma_store_commit();
+      }
+      store_buf ^= 1;
+    } else if (row_ok) {
+      if (p.out_mode == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) +
+                                              (size_t)row * p.ldc + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j * 8 < ncols) dst[j] = pack8(v + j * 8);
+      } else {
+        float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
+        if (p.out_mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j * 4 < ncols)
+              reinterpret_cast<float4*>(dst)[j] =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i < ncols) atomicAdd(dst + i, v[i]);     // RED.ADD.F32 (split-K accumulation)
+        }
+      }
+    }
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -327,7 +436,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
-      if (kb1 <= kb0 && lane == 0) tc_commit(&tmem_full[acc]);   // empty split: publish zeros path
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -344,105 +452,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int n_idx = (tile / p.num_m_blocks) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_idx + q * 32 + lane;
-      const bool row_ok = row < p.M;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 64) {
-        // two x32 loads in flight before the wait: 64 accumulator columns of this lane's row
-        uint32_t r[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
-        tc_ld_32x32b_x32(taddr, r);
-        tc_ld_32x32b_x32(taddr + 32, r + 32);
-        tc_wait_ld();
-        const int col0 = n_idx + c0;
-        if (col0 >= p.N) continue;                       // warp-uniform
-        const int ncols = min(64, p.N - col0);           // N % 8 == 0 is enforced by the host
-        float v[64];
-#pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-        if (p.out_mode != 1 && row_ok) {
-          if (p.bias != nullptr) {
-            const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
-#pragma unroll
-            for (int i = 0; i < 64; ++i)
-              if (i < ncols) v[i] += __bfloat162float(b[i]);
-          } else if (p.bias_f32 != nullptr) {
-            const float* b = reinterpret_cast<const float*>(p.bias_f32) + col0;
-#pragma unroll
-            for (int i = 0; i < 64; ++i)
-              if (i < ncols) v[i] += b[i];
-          }
-          if (p.preact != nullptr) {
-            uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.preact) +
-                                                 (size_t)row * p.ldc + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j * 8 < ncols) pp[j] = pack8(v + j * 8);
-          }
-          if (p.act == 1) {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.0f);
-          } else if (p.act == 2) {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = gelu_erf(v[i]);
-          }
-          if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(
-                reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldc + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (j * 8 < ncols) {
-                float a[8];
-                unpack8(rp[j], a);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                  if (p.act == 3) v[j * 8 + t] *= gelu_erf_grad(a[t]);
-                  else if (p.act == 4) v[j * 8 + t] = a[t] > 0.0f ? v[j * 8 + t] : 0.0f;
-                  else v[j * 8 + t] += a[t];
-                }
-              }
-            }
-          }
-        }
-        if (p.out_mode == 0 && p.tma_store) {
-          // stage 32 rows x 128 B in the 128B-swizzled layout (conflict-free 16 B stores), then one
-          // lane issues a bulk tensor store; TMA clips rows >= M and columns >= N.
-          uint8_t* buf = my_store + store_buf * 4096;
-          if (lane == 0) tma_store_wait_read<1>();       // the store issued 2 chunks ago has read `buf`
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8(v + j * 8);
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&map_c, buf, col0, m_idx + q * 32);
-            tma_store_commit();
-          }
-          store_buf ^= 1;
-        } else if (row_ok) {
-          if (p.out_mode == 0) {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) +
-                                                  (size_t)row * p.ldc + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (j * 8 < ncols) dst[j] = pack8(v + j * 8);
-          } else {
-            float* dst = reinterpret_cast<float*>(p.C) + (size_t)row * p.ldc + col0;
-            if (p.out_mode == 2) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j * 4 < ncols)
-                  reinterpret_cast<float4*>(dst)[j] =
-                      make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 64; ++i)
-                if (i < ncols) atomicAdd(dst + i, v[i]);     // RED.ADD.F32 (split-K accumulation)
-            }
-          }
-        }
-      }
+      epilogue_rows<BN>(p, &map_c, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, my_store, store_buf);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -455,6 +465,236 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// ====================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 tile.  Each CTA
+// owns 128 rows of A and of the accumulator (its own TMEM) and HALF of the B tile (128 of the 256 N
+// rows); the leader's single elected lane issues tcgen05.mma.cta_group::2 (UMMA 256x256x16) which
+// reads A from both CTAs' smem and B halves from both — halving B traffic per CTA.  All TMA loads
+// of both CTAs complete on the LEADER's full barrier; tcgen05.commit multicasts the "stage free" and
+// "accumulator ready" signals to both CTAs; both CTAs' epilogue warps release the accumulator on
+// the leader's tmem_empty barrier.  Arithmetic intensity per CTA: 32 KB of operands per 128x256x64
+// MACs (48 KB in the 1-CTA kernel) — the L2 -> SM path is what bounds large-K GEMMs on B200.
+// ====================================================================================================
+constexpr int BN2 = 256;
+struct Cfg2 {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB : this CTA's 128 rows
+  static constexpr int B_BYTES = (BN2 / 2) * BLOCK_K * 2;        // 16 KB : this CTA's half of B
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int TMEM_COLS = 2 * BN2;
+  static constexpr int STORE_BYTES = 4 * 2 * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the LEADER CTA's copy of a barrier (bit 24 selects the CTA of a pair)
+__device__ __forceinline__ uint32_t leader_addr(const void* p) { return smem_u32(p) & 0xFEFFFFFFu; }
+
+__device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+      "[%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
+  using C = Cfg2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint8_t* smem_store = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_store + C::STORE_BYTES);
+  uint64_t* full_bar = bars;                     // [STAGES]   (used in the leader CTA only)
+  uint64_t* empty_bar = bars + C::STAGES;        // [STAGES]   (per CTA; multicast-committed)
+  uint64_t* tmem_full = bars + 2 * C::STAGES;    // [2]        (per CTA; multicast-committed)
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]        (leader CTA; 8 arrivals = 2 CTAs x 4 warps)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    if (p.tma_store) tma_prefetch_desc(&map_c);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_base_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                 // both CTAs' barriers are initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int num_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);     // 256-row blocks
+  const int tiles = num_m2 * p.num_n_blocks;
+  const int work_items = tiles * p.splits;
+  const int kb_per_split = (p.num_k_blocks + p.splits - 1) / p.splits;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ============================ TMA producer (both CTAs) ============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = cluster_id; w < work_items; w += num_clusters) {
+        const int tile = w % tiles, split = w / tiles;
+        const int m_idx = (tile % num_m2) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
+        const int n_idx = (tile / num_m2) * BN2 + (int)cta_rank * (BN2 / 2);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, p.num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t fb = leader_addr(&full_bar[stage]);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);   // bytes of BOTH CTAs
+          uint8_t* sa = smem_a + stage * C::A_BYTES;
+          uint8_t* sb = smem_b + stage * C::B_BYTES;
+          const int k_idx = kb * BLOCK_K;
+          if (!A_MN) {
+            tma_load_2d_2cta(&map_a, fb, sa, k_idx, m_idx);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 64; ++c)
+              tma_load_2d_2cta(&map_a, fb, sa + c * (BLOCK_K * 128), m_idx + 64 * c, k_idx);
+          }
+          if (!B_MN) {
+            tma_load_2d_2cta(&map_b, fb, sb, k_idx, n_idx);                   // box {64 k, 128 n}
+          } else {
+#pragma unroll
+            for (int c = 0; c < (BN2 / 2) / 64; ++c)
+              tma_load_2d_2cta(&map_b, fb, sb + c * (BLOCK_K * 128), n_idx + 64 * c, k_idx);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer (leader CTA only) ============================
+    if (leader) {
+      uint32_t idesc = 0;
+      idesc |= 1u << 4;
+      idesc |= 1u << 7;
+      idesc |= 1u << 10;
+      idesc |= (A_MN ? 1u : 0u) << 15;
+      idesc |= (B_MN ? 1u : 0u) << 16;
+      idesc |= (uint32_t)(BN2 >> 3) << 17;
+      idesc |= (uint32_t)((2 * BLOCK_M) >> 4) << 24;       // UMMA M = 256 across the CTA pair
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = cluster_id; w < work_items; w += num_clusters) {
+        const int split = w / tiles;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, p.num_k_blocks);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
+            const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                       : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
+              const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                       : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
+              tc_mma_bf16_2cta(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit_2cta(&empty_bar[stage]);                  // frees the stage in BOTH CTAs
+            if (kb == kb1 - 1) tc_commit_2cta(&tmem_full[acc]);  // accumulators ready in BOTH CTAs
+          }
+          __syncwarp();
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ============================ epilogue warps (both CTAs, own 128 rows) ============================
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint8_t* my_store = smem_store + q * (2 * 4096);
+    int store_buf = 0;
+    for (int w = cluster_id; w < work_items; w += num_clusters) {
+      const int tile = w % tiles;
+      const int m_idx = (tile % num_m2) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
+      const int n_idx = (tile / num_m2) * BN2;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_rows<BN2>(p, &map_c, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, my_store, store_buf);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_addr(&tmem_empty[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.tma_store && lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                 // the peer may still read my smem / signal my barriers until here
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)C::TMEM_COLS)
                  : "memory");
   }
@@ -522,6 +762,38 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
   return 0;
 }
 
+template <bool A_MN, bool B_MN>
+int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmParams& p,
+            int max_ctas, cudaStream_t st) {
+  auto kern = gemm_bf16_2cta_kernel<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES);
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);
+    attr_set = true;
+  }
+  const int num_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int work = num_m2 * p.num_n_blocks * p.splits;
+  int clusters = work < g_num_sms / 2 ? work : g_num_sms / 2;
+  if (max_ctas > 1 && clusters > max_ctas / 2) clusters = max_ctas / 2;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg2::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p);
+  if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -535,7 +807,7 @@ const char* b200dp_gemm_last_error() { return g_err; }
 int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                      int a_mn, int b_mn, const void* bias_bf16, const void* bias_f32, const void* residual,
                      void* preact, int act, int out_mode, float alpha, int splits, int block_n, int max_ctas,
-                     unsigned long long stream) {
+                     int two_cta, unsigned long long stream) {
   if (ensure_init()) return -1;
   if (M <= 0 || N <= 0 || K <= 0) return fail("bad shape");
   if ((N % 8) || (lda % 8) || (ldb % 8) || (ldc % 4) || ((out_mode == 0) && (ldc % 8)))
@@ -568,6 +840,14 @@ int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K,
     mc = ma;   // unused
   }
   cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  if (two_cta && BN == 256) {
+    // B map for the pair: each CTA loads half of the 256 N rows (K-major box {64, 128})
+    if (!b_mn && make_map(&mb, B, N, K, ldb, BN2 / 2)) return -1;
+    if (!a_mn && !b_mn) return launch2<false, false>(ma, mb, mc, p, max_ctas, st);
+    if (!a_mn && b_mn) return launch2<false, true>(ma, mb, mc, p, max_ctas, st);
+    if (a_mn && !b_mn) return launch2<true, false>(ma, mb, mc, p, max_ctas, st);
+    return launch2<true, true>(ma, mb, mc, p, max_ctas, st);
+  }
 #define DISPATCH(BNV)                                                                         \
   if (BN == BNV) {                                                                            \
     if (!a_mn && !b_mn) return launch<BNV, false, false>(ma, mb, mc, p, max_ctas, st);            \

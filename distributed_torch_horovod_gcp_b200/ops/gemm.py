@@ -12,6 +12,7 @@ has an activation.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import torch
@@ -29,7 +30,7 @@ def register(lib, have):
     _lib = lib
     vp, i, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.b200dp_gemm_bf16.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, i, i, f, i,
-                                     i, i, ctypes.c_uint64]
+                                     i, i, i, ctypes.c_uint64]
     lib.b200dp_gemm_bf16.restype = i
     lib.b200dp_gemm_last_error.restype = ctypes.c_char_p
     have["gemm"] = True
@@ -40,7 +41,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
          a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, preact: Optional[torch.Tensor] = None,
          act: int = 0, out_mode: int = 0, alpha: float = 1.0, splits: int = 1, block_n: int = 0,
-         max_ctas: int = 0) -> torch.Tensor:
+         max_ctas: int = 0, two_cta: Optional[bool] = None) -> torch.Tensor:
     """Raw kernel call.  ``a``: [M,K] (K-major) or [K,M] (MN-major) bf16 with contiguous rows;
     ``b``: [N,K] or [K,N]; ``out``: [M,N] bf16 (out_mode 0) or fp32 (1: atomic add, 2: store)."""
     assert _lib is not None, "libb200dp_kernels.so not loaded"
@@ -53,12 +54,27 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
         int(a_mn), int(b_mn), bias_bf, bias_f32,
         residual.data_ptr() if residual is not None else None,
         preact.data_ptr() if preact is not None else None,
-        act, out_mode, float(alpha), splits, block_n, max_ctas,
+        act, out_mode, float(alpha), splits, block_n, max_ctas, int(_want_2cta(M, N, K, two_cta)),
         torch.cuda.current_stream(a.device).cuda_stream)
     if rc != 0:
         raise RuntimeError("b200dp_gemm_bf16: " + (_lib.b200dp_gemm_last_error() or b"").decode())
     counters.bump("gemm_sm100")
     return out
+
+
+_TWO_CTA = os.environ.get("B200DP_GEMM_2CTA", "1")
+
+
+def _want_2cta(M: int, N: int, K: int, override: Optional[bool]) -> bool:
+    """cta_group::2 (256x256 tile per CTA pair) pays when the GEMM is operand-bandwidth bound:
+    wide N (the kernel instantiates BN=256 only) and enough rows/depth for the pair to amortise."""
+    if override is not None:
+        return bool(override)
+    if _TWO_CTA == "0":
+        return False
+    if _TWO_CTA == "force":
+        return N > 128
+    return N > 128 and M >= 512 and K >= 256
 
 
 def supported(x: torch.Tensor, weight: torch.Tensor) -> bool:

@@ -1,0 +1,17 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+exec > >(tee gpurun_out/gpu_2cta.log) 2>&1
+python -c "import __graft_entry__ as g; g.build()" > /dev/null 2>&1 || exit 1
+J='import sys,json
+for l in sys.stdin:
+    if l.startswith("{"):
+        d=json.loads(l); print({k:d.get(k) for k in ("impl","value","ms_per_step","gpu_launches")}, d["config"].get("cuda_graph"))
+    elif "rror" in l or "failed" in l: print(l.strip()[:300])'
+echo "== pytest 2cta"; timeout 300 python -m pytest tests/test_gpu_gemm.py -q -m gpu -x -k "2cta" 2>&1 | tail -12
+echo "== pytest gemm all (2cta default)"; timeout 600 python -m pytest tests/test_gpu_gemm.py -q -m gpu 2>&1 | tail -6
+echo "== vit ours 2cta"; timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-e2e --model vit_b_16 --batch 128 2>&1 | python -c "$J"
+echo "== vit ours 1cta"; B200DP_GEMM_2CTA=0 timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-e2e --model vit_b_16 --batch 128 2>&1 | python -c "$J"
+echo "== resnet50 ours 2cta"; timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --no-e2e 2>&1 | python -c "$J"
+echo "== resnet50 ours 1cta"; B200DP_GEMM_2CTA=0 timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --no-e2e 2>&1 | python -c "$J"
+echo "== done"

@@ -247,3 +247,24 @@ def test_layer_norm_matches_torch(R, C):
     assert _rel(x.grad, xr.grad) < 2e-2
     assert _rel(w.grad, wr.grad) < 2e-2
     assert _rel(b.grad, br.grad) < 2e-2
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(512, 256, 256), (25216, 768, 3072), (1000, 2304, 768), (4096, 264, 512)])
+def test_gemm_2cta(a_mn, b_mn, M, N, K):
+    """cta_group::2 kernel (256x256 tile per CTA pair) vs fp32 reference."""
+    g = _k()
+    torch.manual_seed(11)
+    A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16) * 0.5
+    B = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.5
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major needs the row count to be a multiple of 8")
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    g.gemm(a, b, out, M, N, K, a_mn=a_mn, b_mn=b_mn, two_cta=True)
+    assert _rel(out, A.float() @ B.float().t()) < 6e-3
+    # split-K + fp32 atomics through the 2-CTA path
+    acc = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    g.gemm(a, b, acc, M, N, K, a_mn=a_mn, b_mn=b_mn, out_mode=1, splits=3, two_cta=True)
+    assert _rel(acc, A.float() @ B.float().t()) < 3e-3
