@@ -10,7 +10,8 @@
 //   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma, UMMA 128xBNx16,
 //                 accumulator in TMEM, tcgen05.commit releases smem stages / publishes the tile)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b.x32 -> registers -> bias/act/residual -> global)
+//   warps 2..9  : epilogue (tcgen05.ld 32x32b.x32 -> registers -> bias/act/residual -> swizzled smem ->
+//                 TMA bulk store); two warps per TMEM lane quarter, each taking half of the columns
 //   smem ring of kStages {A 128x64, B BNx64} tiles; TMEM double-buffered accumulators so the
 //   epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -28,7 +29,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // 64 bf16 = 128 bytes = one 128B swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;     // 6 warps
+constexpr int NUM_THREADS = 320;     // 10 warps: TMA, MMA, 8 epilogue (2 per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
 
 struct GemmParams {
   int M, N, K;
@@ -168,12 +170,24 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return d;
 }
 
+// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution): 1 rcp + 1 ex2 + 6 fma
+// instead of the ~40-instruction erff — the epilogue, not the MMA, bounds the GELU GEMMs.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float y = 1.0f - poly * t * __expf(-ax * ax);
+  return copysignf(y, x);
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
 }
 
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
@@ -202,9 +216,9 @@ struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 3 : ((BN == 128) ? 5 : 6);
   static constexpr int TMEM_COLS = 2 * BN;       // double-buffered fp32 accumulator
-  static constexpr int STORE_BYTES = 4 * 2 * 4096;   // per epilogue warp: 2 x (32 rows x 128 B) staging
+  static constexpr int STORE_BYTES = EPI_WARPS * 2 * 4096;   // per epilogue warp: out + preact staging (32 rows x 128 B each)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -212,13 +226,14 @@ struct Cfg {
 // registers -> alpha/bias/activation/residual -> bf16 via swizzled smem + TMA bulk store, or fp32
 // store / atomic add.  Shared by the 1-CTA and the 2-CTA (cta_group::2) kernels.
 template <int BN>
-__device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtensorMap* map_c, uint32_t tmem_base,
-                                              int acc, int q, int lane, int m_row0, int n_idx,
-                                              uint8_t* my_store, int& store_buf) {
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtensorMap* map_c,
+                                              const CUtensorMap* map_z, uint32_t tmem_base, int acc, int q,
+                                              int lane, int m_row0, int n_idx, int c_begin, int c_end,
+                                              uint8_t* my_store) {
   const int row = m_row0 + lane;
   const bool row_ok = row < p.M;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 64) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 64) {
     // two x32 loads in flight before the wait: 64 accumulator columns of this lane's row
     uint32_t r[64];
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
@@ -243,12 +258,20 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
         for (int i = 0; i < 64; ++i)
           if (i < ncols) v[i] += b[i];
       }
-      if (p.preact != nullptr) {
+      if (p.preact != nullptr && !(p.out_mode == 0 && p.tma_store)) {
         uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.preact) +
                                              (size_t)row * p.ldc + col0);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (j * 8 < ncols) pp[j] = pack8(v + j * 8);
+      }
+      if (p.preact != nullptr && p.out_mode == 0 && p.tma_store) {
+        // pre-activation tile -> second staging buffer (stored by TMA together with the output)
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(my_store + 4096 + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8(v + j * 8);
       }
       if (p.act == 1) {
 #pragma unroll
@@ -278,8 +301,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
     if (p.out_mode == 0 && p.tma_store) {
       // stage 32 rows x 128 B in the 128B-swizzled layout (conflict-free 16 B stores), then one
       // lane issues a bulk tensor store; TMA clips rows >= M and columns >= N.
-      uint8_t* buf = my_store + store_buf * 4096;
-      if (lane == 0) tma_store_wait_read<1>();       // the store issued 2 chunks ago has read `buf`
+      uint8_t* buf = my_store;
+      if (lane == 0) tma_store_wait_read<0>();           // previous chunk's bulk stores have read the staging
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -288,9 +311,9 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
       __syncwarp();
       if (lane == 0) {
         tma_store_2d(map_c, buf, col0, m_row0);
+        if (p.preact != nullptr) tma_store_2d(map_z, buf + 4096, col0, m_row0);
         tma_store_commit();
       }
-      store_buf ^= 1;
     } else if (row_ok) {
       if (p.out_mode == 0) {
         uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) +
@@ -319,7 +342,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_z,
+                 const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -341,13 +365,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (p.tma_store) tma_prefetch_desc(&map_c);
+    if (p.tma_store && p.preact != nullptr) tma_prefetch_desc(&map_z);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty[i], EPI_WARPS);   // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -444,15 +469,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint8_t* my_store = smem_store + q * (2 * 4096);
-    int store_buf = 0;
+    const int half = (warp - 2) >> 2;             // which half of the columns this warp drains
+    const int c_begin = (BN >= 128) ? half * (BN / 2) : 0;
+    const int c_end = (BN >= 128) ? c_begin + BN / 2 : (half == 0 ? BN : 0);
+    uint8_t* my_store = smem_store + (warp - 2) * (2 * 4096);
     for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
       const int tile = w % tiles;
       const int m_idx = (tile % p.num_m_blocks) * BLOCK_M;
       const int n_idx = (tile / p.num_m_blocks) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_rows<BN>(p, &map_c, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, my_store, store_buf);
+      epilogue_rows<BN>(p, &map_c, &map_z, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, c_begin, c_end,
+                        my_store);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -485,9 +513,9 @@ struct Cfg2 {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB : this CTA's 128 rows
   static constexpr int B_BYTES = (BN2 / 2) * BLOCK_K * 2;        // 16 KB : this CTA's half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 6;
+  static constexpr int STAGES = 5;
   static constexpr int TMEM_COLS = 2 * BN2;
-  static constexpr int STORE_BYTES = 4 * 2 * 4096;
+  static constexpr int STORE_BYTES = EPI_WARPS * 2 * 4096;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 + 256;
 };
 
@@ -535,7 +563,8 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const __grid_constant__ CUtensorMap map_c, const GemmParams p) {
+                      const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_z,
+                      const GemmParams p) {
   using C = Cfg2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -559,13 +588,14 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (p.tma_store) tma_prefetch_desc(&map_c);
+    if (p.tma_store && p.preact != nullptr) tma_prefetch_desc(&map_z);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 2 * EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -674,15 +704,17 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint8_t* my_store = smem_store + q * (2 * 4096);
-    int store_buf = 0;
+    const int half = (warp - 2) >> 2;
+    const int c_begin = half * (BN2 / 2), c_end = c_begin + BN2 / 2;
+    uint8_t* my_store = smem_store + (warp - 2) * (2 * 4096);
     for (int w = cluster_id; w < work_items; w += num_clusters) {
       const int tile = w % tiles;
       const int m_idx = (tile % num_m2) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
       const int n_idx = (tile / num_m2) * BN2;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_rows<BN2>(p, &map_c, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, my_store, store_buf);
+      epilogue_rows<BN2>(p, &map_c, &map_z, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, c_begin, c_end,
+                         my_store);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_addr(&tmem_empty[acc]));
@@ -743,8 +775,8 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint
 }
 
 template <int BN, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmParams& p,
-           int max_ctas, cudaStream_t st) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mz,
+           const GemmParams& p, int max_ctas, cudaStream_t st) {
   using C = Cfg<BN>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
@@ -756,15 +788,15 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
   const int work = p.num_m_blocks * p.num_n_blocks * p.splits;
   int grid = work < g_num_sms ? work : g_num_sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mc, p);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ma, mb, mc, mz, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);
   return 0;
 }
 
 template <bool A_MN, bool B_MN>
-int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const GemmParams& p,
-            int max_ctas, cudaStream_t st) {
+int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mz,
+            const GemmParams& p, int max_ctas, cudaStream_t st) {
   auto kern = gemm_bf16_2cta_kernel<A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -789,7 +821,7 @@ int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mz, p);
   if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);
   return 0;
 }
@@ -831,7 +863,7 @@ int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K,
   p.act = act; p.out_mode = out_mode; p.C = C; p.bias = bias_bf16; p.bias_f32 = bias_f32;
   p.residual = residual; p.preact = preact; p.alpha = alpha;
   p.tma_store = (out_mode == 0) ? 1 : 0;
-  CUtensorMap ma, mb, mc;
+  CUtensorMap ma, mb, mc, mz;
   if (a_mn ? make_map(&ma, A, K, M, lda, BLOCK_K) : make_map(&ma, A, M, K, lda, BLOCK_M)) return -1;
   if (b_mn ? make_map(&mb, B, K, N, ldb, BLOCK_K) : make_map(&mb, B, N, K, ldb, BN)) return -1;
   if (p.tma_store) {
@@ -839,21 +871,26 @@ int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K,
   } else {
     mc = ma;   // unused
   }
+  if (p.tma_store && preact != nullptr) {
+    if (make_map(&mz, preact, M, N, ldc, 32)) return -1;
+  } else {
+    mz = mc;   // unused
+  }
   cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
   if (two_cta && BN == 256) {
     // B map for the pair: each CTA loads half of the 256 N rows (K-major box {64, 128})
     if (!b_mn && make_map(&mb, B, N, K, ldb, BN2 / 2)) return -1;
-    if (!a_mn && !b_mn) return launch2<false, false>(ma, mb, mc, p, max_ctas, st);
-    if (!a_mn && b_mn) return launch2<false, true>(ma, mb, mc, p, max_ctas, st);
-    if (a_mn && !b_mn) return launch2<true, false>(ma, mb, mc, p, max_ctas, st);
-    return launch2<true, true>(ma, mb, mc, p, max_ctas, st);
+    if (!a_mn && !b_mn) return launch2<false, false>(ma, mb, mc, mz, p, max_ctas, st);
+    if (!a_mn && b_mn) return launch2<false, true>(ma, mb, mc, mz, p, max_ctas, st);
+    if (a_mn && !b_mn) return launch2<true, false>(ma, mb, mc, mz, p, max_ctas, st);
+    return launch2<true, true>(ma, mb, mc, mz, p, max_ctas, st);
   }
 #define DISPATCH(BNV)                                                                         \
   if (BN == BNV) {                                                                            \
-    if (!a_mn && !b_mn) return launch<BNV, false, false>(ma, mb, mc, p, max_ctas, st);            \
-    if (!a_mn && b_mn) return launch<BNV, false, true>(ma, mb, mc, p, max_ctas, st);              \
-    if (a_mn && !b_mn) return launch<BNV, true, false>(ma, mb, mc, p, max_ctas, st);              \
-    return launch<BNV, true, true>(ma, mb, mc, p, max_ctas, st);                                  \
+    if (!a_mn && !b_mn) return launch<BNV, false, false>(ma, mb, mc, mz, p, max_ctas, st);            \
+    if (!a_mn && b_mn) return launch<BNV, false, true>(ma, mb, mc, mz, p, max_ctas, st);              \
+    if (a_mn && !b_mn) return launch<BNV, true, false>(ma, mb, mc, mz, p, max_ctas, st);              \
+    return launch<BNV, true, true>(ma, mb, mc, mz, p, max_ctas, st);                                  \
   }
   DISPATCH(64)
   DISPATCH(128)
