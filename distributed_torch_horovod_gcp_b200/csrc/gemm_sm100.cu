@@ -64,9 +64,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // try_wait suspends for a bounded time per attempt; the attempt counter turns a protocol bug
-  // (lost arrive / wrong phase) into a trap ("unspecified launch failure") instead of a GPU hang.
+  // try_wait suspends for a bounded time per attempt; a %globaltimer watchdog (4 s) turns a protocol
+  // bug (lost arrive / wrong phase) into a trap ("unspecified launch failure") instead of a GPU hang.
   uint32_t done = 0;
+  unsigned long long t0 = 0;
   for (uint32_t tries = 0; !done; ++tries) {
     asm volatile(
         "{\n\t"
@@ -77,7 +78,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
-    if (!done && tries > (1u << 24)) __trap();
+    if (!done && (tries & 1023u) == 1023u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
@@ -246,7 +252,9 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
     float v[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-    if (p.out_mode != 1 && row_ok) {
+    // NOTE: everything in this block that is warp-collective (__syncwarp, staging) must be reached by
+    // all 32 lanes, so only the per-row global accesses are predicated on row_ok.
+    if (p.out_mode != 1) {
       if (p.bias != nullptr) {
         const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
 #pragma unroll
@@ -258,7 +266,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
         for (int i = 0; i < 64; ++i)
           if (i < ncols) v[i] += b[i];
       }
-      if (p.preact != nullptr && !(p.out_mode == 0 && p.tma_store)) {
+      if (p.preact != nullptr && !(p.out_mode == 0 && p.tma_store) && row_ok) {
         uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.preact) +
                                              (size_t)row * p.ldc + col0);
 #pragma unroll
@@ -280,7 +288,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
 #pragma unroll
         for (int i = 0; i < 64; ++i) v[i] = gelu_erf(v[i]);
       }
-      if (p.residual != nullptr) {
+      if (p.residual != nullptr && row_ok) {
         const uint4* rp = reinterpret_cast<const uint4*>(
             reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldc + col0);
 #pragma unroll
