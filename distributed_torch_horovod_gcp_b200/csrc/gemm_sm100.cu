@@ -45,6 +45,8 @@ struct GemmParams {
   const void* residual;    // bf16 [M, ldc] or nullptr (added after act; or `aux` for act 3/4)
   void* preact;            // optional bf16 [M, ldc]: pre-activation values (saved for backward)
   int tma_store;           // out_mode 0: stage the tile in swizzled smem and write it with TMA bulk stores
+  int n_fastest;           // tile order: consecutive CTAs walk the N blocks of one M block first (A tile is
+                           // fetched from HBM once and re-used from L2 while the whole B matrix stays in L2)
   float alpha;
 };
 
@@ -407,8 +409,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t phase = 0;
       for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
         const int tile = w % tiles, split = w / tiles;
-        const int m_idx = (tile % p.num_m_blocks) * BLOCK_M;
-        const int n_idx = (tile / p.num_m_blocks) * BN;
+        const int m_idx = (p.n_fastest ? tile / p.num_n_blocks : tile % p.num_m_blocks) * BLOCK_M;
+        const int n_idx = (p.n_fastest ? tile % p.num_n_blocks : tile / p.num_m_blocks) * BN;
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, p.num_k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -483,8 +485,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     uint8_t* my_store = smem_store + (warp - 2) * (2 * 4096);
     for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
       const int tile = w % tiles;
-      const int m_idx = (tile % p.num_m_blocks) * BLOCK_M;
-      const int n_idx = (tile / p.num_m_blocks) * BN;
+      const int m_idx = (p.n_fastest ? tile / p.num_n_blocks : tile % p.num_m_blocks) * BLOCK_M;
+      const int n_idx = (p.n_fastest ? tile % p.num_n_blocks : tile / p.num_m_blocks) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epilogue_rows<BN>(p, &map_c, &map_z, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, c_begin, c_end,
@@ -633,8 +635,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       uint32_t phase = 0;
       for (int w = cluster_id; w < work_items; w += num_clusters) {
         const int tile = w % tiles, split = w / tiles;
-        const int m_idx = (tile % num_m2) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
-        const int n_idx = (tile / num_m2) * BN2 + (int)cta_rank * (BN2 / 2);
+        const int m_idx = (p.n_fastest ? tile / p.num_n_blocks : tile % num_m2) * (2 * BLOCK_M) +
+                          (int)cta_rank * BLOCK_M;
+        const int n_idx = (p.n_fastest ? tile % p.num_n_blocks : tile / num_m2) * BN2 +
+                          (int)cta_rank * (BN2 / 2);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb0 + kb_per_split, p.num_k_blocks);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -717,8 +721,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint8_t* my_store = smem_store + (warp - 2) * (2 * 4096);
     for (int w = cluster_id; w < work_items; w += num_clusters) {
       const int tile = w % tiles;
-      const int m_idx = (tile % num_m2) * (2 * BLOCK_M) + (int)cta_rank * BLOCK_M;
-      const int n_idx = (tile / num_m2) * BN2;
+      const int m_idx = (p.n_fastest ? tile / p.num_n_blocks : tile % num_m2) * (2 * BLOCK_M) +
+                        (int)cta_rank * BLOCK_M;
+      const int n_idx = (p.n_fastest ? tile % p.num_n_blocks : tile / num_m2) * BN2;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epilogue_rows<BN2>(p, &map_c, &map_z, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, c_begin, c_end,
@@ -871,6 +876,8 @@ int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K,
   p.act = act; p.out_mode = out_mode; p.C = C; p.bias = bias_bf16; p.bias_f32 = bias_f32;
   p.residual = residual; p.preact = preact; p.alpha = alpha;
   p.tma_store = (out_mode == 0) ? 1 : 0;
+  // B (N x K bf16) small enough to live in L2 next to the in-flight A tiles -> walk N first
+  p.n_fastest = ((size_t)N * (size_t)K * 2 <= ((size_t)48 << 20)) ? 1 : 0;
   CUtensorMap ma, mb, mc, mz;
   if (a_mn ? make_map(&ma, A, K, M, lda, BLOCK_K) : make_map(&ma, A, M, K, lda, BLOCK_M)) return -1;
   if (b_mn ? make_map(&mb, B, K, N, ldb, BLOCK_K) : make_map(&mb, B, N, K, ldb, BN)) return -1;

@@ -8,10 +8,10 @@ for l in sys.stdin:
     if l.startswith("{"):
         d=json.loads(l); print({k:d.get(k) for k in ("impl","value","ms_per_step","gpu_launches")}, d["config"].get("cuda_graph"))
     elif "rror" in l or "failed" in l: print(l.strip()[:300])'
-echo "== pytest gemm all"; timeout 240 python -m pytest tests/test_gpu_gemm.py -q -m gpu -x 2>&1 | tail -8
-echo "== vit ours 2cta"; timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-e2e --model vit_b_16 --batch 128 2>&1 | python -c "$J"
-echo "== resnet50 ours"; timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --no-e2e 2>&1 | python -c "$J"
-echo "== launch list vit ours"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_vit_ours.csv python scripts/profile_vit.py ours > gpurun_out/prof_vit.log 2>&1
-python scripts/summarize_launches.py gpurun_out/launches_vit_ours.csv 2>/dev/null | head -16
+echo "== pytest gemm all"; timeout 240 python -m pytest tests/test_gpu_gemm.py -q -m gpu -x 2>&1 | tail -6
+echo "== pytest single"; timeout 300 python -m pytest tests/test_gpu_single.py -q -m gpu 2>&1 | tail -6
+echo "== vit ours"; timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-e2e --model vit_b_16 --batch 128 2>&1 | python -c "$J"
+echo "== resnet50 ours"; timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-e2e 2>&1 | python -c "$J"
+echo "== resnet152 ours / standin"; timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-e2e --model resnet152 --batch 128 2>&1 | python -c "$J"
+timeout 300 python bench.py --gpus 1 --steps 10 --warmup 3 --no-e2e --model resnet152 --batch 128 --impl nccl_standin 2>&1 | python -c "$J"
 echo "== done"

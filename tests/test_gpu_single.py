@@ -104,3 +104,51 @@ def test_lstm_fused_head_matches_torch():
     F.mse_loss(out_ref, y).backward()
     for (n, a), (_, b) in zip(m.named_parameters(), ref.named_parameters()):
         torch.testing.assert_close(a.grad, b.grad, rtol=2e-3, atol=1e-5, msg=lambda s: f"{n}: {s}")
+
+
+def test_cuda_graph_step_matches_eager(hvd_single, monkeypatch):
+    """Whole-step CUDA-graph capture (fwd + bwd + fused update kernels) == eager execution."""
+    import copy
+    monkeypatch.setenv("B200DP_FUSED_SINGLE", "1")
+    hvd = hvd_single
+    from distributed_torch_horovod_gcp_b200.utils.graph import GraphedStep
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    base = torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.ReLU(), torch.nn.Linear(128, 8)).to(dev)
+    models = [copy.deepcopy(base) for _ in range(2)]
+    opts = [hvd.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9),
+                                     named_parameters=m.named_parameters()) for m in models]
+    assert all(o.fused_engine is not None for o in opts)
+
+    def make_step(m, o):
+        def step(x, y):
+            loss = F.mse_loss(m(x), y)
+            loss.backward()
+            o.step()
+            o.zero_grad()
+            return loss.detach()
+        return step
+
+    xs = [torch.randn(16, 64, device=dev) for _ in range(6)]
+    ys = [torch.randn(16, 8, device=dev) for _ in range(6)]
+    eager = make_step(models[0], opts[0])
+    graphed = GraphedStep(make_step(models[1], opts[1]), [xs[0], ys[0]], warmup=2)
+    assert graphed.kernels_per_replay >= 1
+    for _ in range(2):                       # replicate the graph's warm-up updates on the eager model
+        eager(xs[0], ys[0])
+    eager(xs[0], ys[0])                      # the captured step itself also executed once during capture? no:
+    # capture does not execute; undo the extra eager step by re-syncing parameters instead
+    with torch.no_grad():
+        for a, b in zip(models[0].parameters(), models[1].parameters()):
+            a.copy_(b)
+    opts[0].fused_engine.params_changed()
+    for ar0, ar1 in zip(opts[0].fused_engine.arenas.values(), opts[1].fused_engine.arenas.values()):
+        ar0["S0"].copy_(ar1["S0"])
+    opts[0].fused_engine.step_ctr.copy_(opts[1].fused_engine.step_ctr)
+    for x, y in zip(xs, ys):
+        le = eager(x, y)
+        lg = graphed(x, y)
+        torch.testing.assert_close(le, lg, rtol=1e-5, atol=1e-6)
+    torch.cuda.synchronize()
+    for a, b in zip(models[0].parameters(), models[1].parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
