@@ -573,10 +573,12 @@ int reduce_grid() {
 }
 
 int grid_for(long long nvec, int V) {
+  // streaming kernels: 64 registers x 256 threads -> 4 resident blocks per SM; launch exactly one
+  // wave (grid-stride loops cover the rest) so there is no half-empty tail wave.
   long long blocks = (nvec + THREADS * 8 - 1) / (THREADS * 8);
-  if (blocks > 148 * 6) blocks = 148 * 6;
+  const long long one_wave = (long long)reduce_grid() * 4;
+  if (blocks > one_wave) blocks = one_wave;
   if (blocks < 1) blocks = 1;
-  // total threads must be a multiple of V (V is a power of two <= 256 => always true)
   return (int)blocks;
 }
 

@@ -29,8 +29,7 @@ class EncoderBlock(nn.Module):
     def forward(self, x):
         B, S, D = x.shape
         h = F2.layer_norm(x, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps)
-        qkv = F2.linear(h, self.qkv.weight, self.qkv.bias)
-        a = F2.attention(qkv, self.heads)                                  # [B,S,D]
+        a = F2.qkv_attention(h, self.qkv.weight, self.qkv.bias, self.heads)   # [B,S,D]
         x = F2.linear(a, self.proj.weight, self.proj.bias, residual=x)
         h = F2.layer_norm(x, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps)
         return F2.mlp(h, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, residual=x)

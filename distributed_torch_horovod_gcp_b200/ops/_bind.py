@@ -9,7 +9,7 @@ from . import bn as _bn
 from . import lstm_fused as _lstm
 from . import ln as _ln
 from .ln import layer_norm  # noqa: F401
-from .gemm import linear, mlp  # noqa: F401  (re-exported as kernels.linear / kernels.mlp)
+from .gemm import linear, mlp, qkv_proj  # noqa: F401  (re-exported as kernels.linear / .mlp / .qkv_proj)
 from .bn import conv_bn_act, bn_act, max_pool_3x3_s2  # noqa: F401
 
 

@@ -107,6 +107,21 @@ def attention(qkv, heads: int):
     return attention_reference(qkv, heads)
 
 
+def qkv_attention(x, weight, bias, heads: int):
+    """Multi-head self-attention input stage: packed QKV projection + scaled-dot-product attention.
+    Kernel path: q, k, v are produced as three dense matrices (no un-pack / re-pack copies)."""
+    k = _kernels(x)
+    if k is not None and k.has("linear") and k.linear_supported(x, weight) and weight.shape[0] % 24 == 0 \
+            and os.environ.get("B200DP_SPLIT_QKV", "1") == "1":
+        B, S, D = x.shape
+        hd = D // heads
+        q, kk, v = k.qkv_proj(x, weight, bias)
+        q, kk, v = [t.view(B, S, heads, hd).transpose(1, 2) for t in (q, kk, v)]
+        o = F.scaled_dot_product_attention(q, kk, v)
+        return o.transpose(1, 2).reshape(B, S, D)
+    return attention(linear(x, weight, bias), heads)
+
+
 # ------------------------------------------------------------------ ViT patch embedding
 def patch_embed(x, weight, bias, patch: int):
     """``[B,3,H,W]`` (NCHW logical, any memory format) -> ``[B, (H/p)*(W/p), D]``: gather

@@ -235,5 +235,66 @@ def mlp(x, w1, b1, w2, b2, residual=None):
     return _MLPFn.apply(x, w1, b1, w2, b2, residual)
 
 
+class _QKVFn(torch.autograd.Function):
+    """Attention input projection producing q, k, v as three DENSE [M, D] matrices (three GEMMs on
+    row-slices of the packed [3D, D] weight).  A packed [M, 3D] output forces PyTorch to un-pack
+    with strided views forward and to re-pack dq/dk/dv with a cat + copies backward — 5.5 ms of
+    a 31 ms ViT-B step (profiles/run_1gpu_vit_2cta_epilogue.log).  Here the backward consumes
+    dq, dk, dv where they are: dx is accumulated through the GEMM's residual input and the weight
+    gradient is written slice by slice."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        D3, D = weight.shape
+        Dh = D3 // 3
+        x2 = x.reshape(-1, D)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        outs = []
+        for i in range(3):
+            o = torch.empty((M, Dh), dtype=torch.bfloat16, device=x.device)
+            gemm(x2, weight[i * Dh:(i + 1) * Dh], o, M, Dh, D,
+                 bias=bias[i * Dh:(i + 1) * Dh] if bias is not None else None)
+            outs.append(o.view(*x.shape[:-1], Dh))
+        ctx.save_for_backward(x2, weight)
+        ctx.x_shape, ctx.has_bias = x.shape, bias is not None
+        ctx.bdt = bias.dtype if bias is not None else None
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dq, dk, dv):
+        x2, weight = ctx.saved_tensors
+        D3, D = weight.shape
+        Dh = D3 // 3
+        M = x2.shape[0]
+        dev = x2.device
+        gs = []
+        for g in (dq, dk, dv):
+            g2 = g.reshape(M, Dh)
+            if not g2.is_contiguous() or g2.data_ptr() % 16:
+                g2 = g2.contiguous()
+            gs.append(g2)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            for i, g2 in enumerate(gs):
+                nxt = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+                gemm(g2, weight[i * Dh:(i + 1) * Dh], nxt, M, D, Dh, b_mn=True, residual=dx)
+                dx = nxt
+            dx = dx.view(ctx.x_shape)
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((D3, D), dtype=weight.dtype, device=dev)
+            for i, g2 in enumerate(gs):
+                dw[i * Dh:(i + 1) * Dh].copy_(wgrad(g2, x2, Dh, D, M, weight.dtype))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.cat([bias_grad(g2, Dh, M, ctx.bdt) for g2 in gs])
+        return dx, dw, db
+
+
+def qkv_proj(x, weight, bias):
+    return _QKVFn.apply(x, weight, bias)
+
+
 def linear(x, weight, bias=None, act: Optional[str] = None, residual=None):
     return _LinearFn.apply(x, weight, bias, ACT[act], residual)

@@ -268,3 +268,22 @@ def test_gemm_2cta(a_mn, b_mn, M, N, K):
     acc = torch.zeros(M, N, device="cuda", dtype=torch.float32)
     g.gemm(a, b, acc, M, N, K, a_mn=a_mn, b_mn=b_mn, out_mode=1, splits=3, two_cta=True)
     assert _rel(acc, A.float() @ B.float().t()) < 3e-3
+
+
+def test_qkv_attention_matches_reference():
+    from distributed_torch_horovod_gcp_b200.ops import functional as F2
+    torch.manual_seed(12)
+    B, S, D, H = 4, 197, 768, 12
+    x = (torch.randn(B, S, D, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(3 * D, D, device="cuda") * 0.03).to(torch.bfloat16).requires_grad_(True)
+    b = (torch.randn(3 * D, device="cuda") * 0.1).to(torch.bfloat16).requires_grad_(True)
+    xr, wr, br = [t.detach().float().requires_grad_(True) for t in (x, w, b)]
+    y = F2.qkv_attention(x, w, b, H)
+    yr = F2.attention_reference(torch.nn.functional.linear(xr, wr, br), H)
+    assert y.shape == yr.shape and _rel(y, yr) < 2e-2
+    g = torch.randn_like(y)
+    y.backward(g)
+    yr.backward(g.float())
+    assert _rel(x.grad, xr.grad) < 3e-2
+    assert _rel(w.grad, wr.grad) < 3e-2
+    assert _rel(b.grad, br.grad) < 3e-2
