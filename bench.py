@@ -24,7 +24,6 @@ import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -91,7 +90,6 @@ def main():
     if args.impl == "nccl_standin":
         os.environ["B200DP_REFERENCE_OPS"] = "1"     # library cuDNN/cuBLAS ops only
     import torch
-    import torch.distributed as dist
     import torch.nn.functional as F
 
     import distributed_torch_horovod_gcp_b200.torch as hvd

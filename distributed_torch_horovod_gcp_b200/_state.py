@@ -124,7 +124,7 @@ def init(comm=None, process_sets=None) -> None:
         tl = os.environ.get("HOROVOD_TIMELINE") or os.environ.get("B200DP_TIMELINE")
         if tl:
             from .utils.timeline import Timeline
-            rt.timeline = Timeline(tl if size == 1 or "{rank}" in tl else tl, rank)
+            rt.timeline = Timeline(tl, rank)
 
 
 def shutdown() -> None:

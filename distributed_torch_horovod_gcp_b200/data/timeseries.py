@@ -19,7 +19,7 @@ zero-copy ``sliding_window_view``.
 from __future__ import annotations
 
 import os
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence
 
 import numpy as np
 import torch

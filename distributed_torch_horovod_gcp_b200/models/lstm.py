@@ -18,7 +18,7 @@ B200-first changes:
 from __future__ import annotations
 
 import warnings
-from typing import Callable, List, Optional, Sequence
+from typing import Callable, Optional, Sequence
 
 import torch
 from torch import nn

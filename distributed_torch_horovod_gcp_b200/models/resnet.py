@@ -14,9 +14,8 @@ unit; the PyTorch composition is the fallback and the numerics oracle.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Type, Union
+from typing import List, Type, Union
 
-import torch
 from torch import nn
 
 from ..ops import functional as F2

@@ -19,10 +19,8 @@ Memory plan (per dtype arena, same element layout in every arena):
 """
 from __future__ import annotations
 
-import ctypes
-import os
 import weakref
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 import torch
 import torch.distributed as dist

@@ -12,7 +12,7 @@ from __future__ import annotations
 import collections
 import io
 import pickle
-from typing import Dict, Iterable, List, Tuple
+from typing import Dict, List, Tuple
 
 import torch
 import torch.distributed as dist

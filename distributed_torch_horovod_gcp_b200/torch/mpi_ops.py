@@ -19,7 +19,7 @@ from __future__ import annotations
 import itertools
 import os
 import threading
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist

@@ -6,7 +6,6 @@ from __future__ import annotations
 import statistics
 import subprocess
 import threading
-import time
 from typing import Dict, List, Optional
 
 _REASONS = {

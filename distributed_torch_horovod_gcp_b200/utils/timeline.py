@@ -13,7 +13,7 @@ import json
 import os
 import threading
 import time
-from typing import List, Optional
+from typing import List
 
 
 class Timeline:

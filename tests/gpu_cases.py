@@ -240,3 +240,32 @@ def stress_flag_reuse(hvd, iters):
     s.check_errors()
     assert bad == 0, bad
     return True
+
+
+def watchdog_timeout(hvd):
+    """Failure detection: a rank that never joins a collective must not hang its
+    peers' GPUs — the bounded spin-wait expires, the kernel reports through the host mailbox and
+    the host raises HorovodInternalError naming the straggler."""
+    import time
+    s = _symm(hvd)
+    r = hvd.rank()
+    t = hvd.symm_empty(1 << 12, torch.float32)
+    t.fill_(1.0)
+    hvd.allreduce_(t, op=hvd.Sum)                 # one healthy collective first
+    torch.cuda.synchronize()
+    s.check_errors()
+    raised = False
+    if r != 1:
+        t0 = time.time()
+        hvd.allreduce_(t, op=hvd.Sum)             # rank 1 never shows up
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        try:
+            s.check_errors()
+        except hvd.HorovodInternalError as e:
+            raised = "timed out waiting for rank" in str(e)
+        assert raised, "watchdog did not fire"
+        assert dt < 30, dt
+    else:
+        time.sleep(6)
+    return raised or r == 1

@@ -22,7 +22,7 @@ def _entry(rank, world, port, modname, fname, args, q, cuda=False):
                        "MASTER_PORT": str(port), "OMP_NUM_THREADS": "1"})
     if cuda:
         os.environ.pop("B200DP_FORCE_CPU", None)
-        os.environ.setdefault("B200DP_KERNEL_TIMEOUT_S", "10")
+        os.environ.setdefault("B200DP_KERNEL_TIMEOUT_S", "10")   # inherited from the test if it set one
     else:
         os.environ["B200DP_FORCE_CPU"] = "1"
     sys.path.insert(0, ROOT)

@@ -46,3 +46,9 @@ def test_lstm_dp_training():
 def test_stress_flag_reuse():
     assert all(run_workers(_world(), "gpu_cases", "stress_flag_reuse", (2000,), cuda=True,
                            timeout=600))
+
+
+def test_watchdog_reports_missing_rank(monkeypatch):
+    monkeypatch.setenv("B200DP_KERNEL_TIMEOUT_S", "3")
+    res = run_workers(2, "gpu_cases", "watchdog_timeout", cuda=True, timeout=300)
+    assert all(res)
