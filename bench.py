@@ -247,7 +247,10 @@ def main():
                              ">> 126 MB L2",
                        "comm": (opt.fused_engine.algorithms() if args.impl == "ours" and
                                 getattr(opt, "fused_engine", None) is not None else
-                                ("nccl-ddp" if world > 1 else "none"))},
+                                ("none" if world == 1 else
+                                 ("nccl-ddp" if args.impl != "ours" else
+                                  "NCCL FALLBACK (symmetric runtime unavailable): bucketed allreduce"
+                                  " + torch optimizer")))},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "final_loss": round(final_loss, 4),
         }
