@@ -47,6 +47,7 @@ def broadcast_parameters(params, root_rank: int, process_set=None) -> None:
     rt = _state._require_init()
     items = _named_tensors(params)
     if mpi_ops._ps_size(process_set) == 1 or not items:
+        _refresh_engines()
         return
     # fused path: pack by (dtype, device) -> one broadcast each
     groups: Dict[Tuple, List[torch.Tensor]] = collections.OrderedDict()
@@ -70,7 +71,13 @@ def broadcast_parameters(params, root_rank: int, process_set=None) -> None:
                 n = t.numel()
                 t.copy_(flat[off:off + n].view_as(t))
                 off += n
-    # parameters may live in a fused engine's symmetric arena with a separate fp32 master
+    _refresh_engines()
+
+
+def _refresh_engines() -> None:
+    """Parameters may live in a fused engine's arena with a separate fp32 master copy: after
+    they were (re)written from outside — this broadcast, or a checkpoint load followed by the
+    customary ``broadcast_parameters`` — the masters are refreshed from the parameters."""
     from ..parallel.fused_engine import live_engines
     for eng in live_engines():
         eng.params_changed()

@@ -352,6 +352,21 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 if s.param.grad is None:
                     self._ensure_view(b, s.param)
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def state_dict(self):
+        """Same layout as the wrapped optimizer's ``state_dict()``.  With the fused engine the
+        momentum / Adam moments live in flat fp32 arenas (sharded by slice for the two-shot/NVLS
+        buckets); they are gathered and exposed as ordinary per-parameter entries first, so
+        "rank 0 saves" checkpointing works unchanged."""
+        if self._engine is not None:
+            self._engine.export_state()
+        return super(self.__class__, self).state_dict()
+
+    def load_state_dict(self, state_dict):
+        super(self.__class__, self).load_state_dict(state_dict)
+        if self._engine is not None:
+            self._engine.import_state()
+
     # ------------------------------------------------------------------ misc
     @property
     def fused_engine(self):
