@@ -92,6 +92,59 @@ class TorchState(State):
         super().sync()
 
 
+class ObjectState(State):
+    """State of arbitrary picklable python objects (Horovod ``hvd.elastic.ObjectState``)."""
+
+
+class ElasticSampler(torch.utils.data.Sampler):
+    """Sharded sampler that remembers which indices were already processed in the current epoch,
+    so that after a reset (rollback / world-size change) the remaining samples are re-partitioned
+    over the new set of ranks (Horovod ``hvd.elastic.ElasticSampler`` shape)."""
+
+    def __init__(self, dataset, shuffle: bool = True, seed: int = 0):
+        self.dataset, self.shuffle, self.seed = dataset, shuffle, seed
+        self.epoch = 0
+        self.processed_indices = set()
+        self.reset()
+
+    def set_epoch(self, epoch: int):
+        self.epoch = epoch
+        self.processed_indices = set()
+        self.reset()
+
+    def record_batch(self, batch_idx: int, batch_size: int):
+        lo = batch_idx * batch_size
+        self.processed_indices.update(self.indices[lo: lo + batch_size])
+
+    def load_state_dict(self, sd):
+        self.epoch = sd["epoch"]
+        self.processed_indices = set(sd["processed_indices"])
+        self.reset()
+
+    def state_dict(self):
+        return {"epoch": self.epoch, "processed_indices": sorted(self.processed_indices)}
+
+    def reset(self):
+        from .. import _state
+        self.num_replicas = _state.size() if _state.is_initialized() else 1
+        self.rank = _state.rank() if _state.is_initialized() else 0
+        remaining = [i for i in range(len(self.dataset)) if i not in self.processed_indices]
+        if self.shuffle:
+            g = torch.Generator().manual_seed(self.seed + self.epoch)
+            perm = torch.randperm(len(remaining), generator=g).tolist()
+            remaining = [remaining[i] for i in perm]
+        self.num_samples = -(-len(remaining) // self.num_replicas) if remaining else 0
+        total = self.num_samples * self.num_replicas
+        remaining += remaining[: total - len(remaining)]
+        self.indices = remaining[self.rank: total: self.num_replicas]
+
+    def __iter__(self):
+        return iter(self.indices)
+
+    def __len__(self):
+        return len(self.indices)
+
+
 def run(func):
     """Decorator: ``func(state, *args)`` is retried from the last commit after a collective
     failure.  ``B200DP_ELASTIC_MAX_RETRIES`` bounds the retries (default 3)."""

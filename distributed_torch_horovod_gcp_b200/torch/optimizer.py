@@ -216,6 +216,9 @@ class _DistributedOptimizer(torch.optim.Optimizer):
 
     # ------------------------------------------------------------------ launch / sync
     def _launch_bucket(self, b: Bucket):
+        tl = _state.runtime().timeline
+        if tl is not None:
+            tl.mark(f"bucket.{b.index}", "BUCKET_READY", bytes=b.nbytes, tensors=len(b.slots))
         if self._engine is not None:
             self._launched[b.index] = self._engine.launch(b)
             return
@@ -304,6 +307,16 @@ class _DistributedOptimizer(torch.optim.Optimizer):
     def step(self, closure=None):
         if not self._active:
             return super(self.__class__, self).step(closure)
+        tl = _state.runtime().timeline
+        if tl is None:
+            return self._step_impl(closure)
+        tl.begin("optimizer", "STEP")
+        try:
+            return self._step_impl(closure)
+        finally:
+            tl.end("optimizer", "STEP")
+
+    def _step_impl(self, closure=None):
         if self._should_synchronize:
             if self._synchronized:
                 warnings.warn("optimizer.step() called without optimizer.skip_synchronize() "

@@ -236,3 +236,31 @@ def sync_batch_norm(hvd):
     torch.testing.assert_close(bn.running_mean, ref.running_mean, rtol=1e-4, atol=1e-6)
     torch.testing.assert_close(bn.running_var, ref.running_var, rtol=1e-4, atol=1e-6)
     return True
+
+
+def timeline_and_elastic(hvd, tmpdir):
+    import json, os
+    path = os.path.join(tmpdir, "tl.json")
+    hvd.start_timeline(path)
+    m = _model(0)
+    opt = hvd.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1),
+                                   named_parameters=m.named_parameters())
+    hvd.broadcast_parameters(m.state_dict(), 0)
+    m(torch.randn(4, 6)).sum().backward()
+    opt.step()
+    opt.zero_grad()
+    hvd.stop_timeline()
+    f = path if hvd.rank() == 0 else f"{path}.rank{hvd.rank()}"
+    names = [e["name"] for e in json.load(open(f))["traceEvents"]]
+    assert "BUCKET_READY" in names and "ALLREDUCE_BEGIN" in names and names.count("STEP") == 2
+    # elastic sampler partitions the not-yet-processed samples over the ranks
+    s = hvd.elastic.ElasticSampler(list(range(20)), shuffle=False)
+    assert len(s) == 20 // hvd.size() and list(s)[0] == hvd.rank()
+    s.record_batch(0, 2)
+    s.reset()
+    assert len(s) == (20 - 2 + hvd.size() - 1) // hvd.size()
+    st = hvd.elastic.ObjectState(epoch=3)
+    st.epoch = 7 if hvd.rank() == 0 else 1
+    st.sync()
+    assert st.epoch == 7
+    return True

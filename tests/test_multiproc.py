@@ -29,3 +29,7 @@ def test_broadcast_optimizer_state():
 
 def test_sync_batch_norm():
     assert all(run_workers(2, "mp_cases", "sync_batch_norm"))
+
+
+def test_timeline_and_elastic(tmp_path):
+    assert all(run_workers(2, "mp_cases", "timeline_and_elastic", (str(tmp_path),)))
