@@ -34,6 +34,9 @@ def main():
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--out", default="")
     ap.add_argument("--algos", default="auto,oneshot,twoshot,nvls,nccl")
+    ap.add_argument("--write-tuning", default="",
+                    help="derive the algorithm table for this world size from the sweep and write "
+                         "it as JSON (load with B200DP_TUNING_FILE)")
     args = ap.parse_args()
 
     hvd.init()
@@ -106,6 +109,15 @@ def main():
                        "roofline_GBs": {"nvlink_nominal_per_dir": 900, "peer_copy_measured": 770,
                                         "nccl_8rank_1GiB_measured": 725},
                        "rows": rows}, f, indent=1)
+    if rank == 0 and args.write_tuning:
+        from distributed_torch_horovod_gcp_b200.runtime import tuning
+        tab = {}
+        if os.path.exists(args.write_tuning):
+            with open(args.write_tuning) as f:
+                tab = json.load(f)
+        tab[str(world)] = tuning.derive_from_sweep(rows, world, bool(symm.multicast))
+        with open(args.write_tuning, "w") as f:
+            json.dump(tab, f, indent=1)
     hvd.shutdown()
 
 

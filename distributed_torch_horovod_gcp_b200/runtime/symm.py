@@ -326,14 +326,11 @@ class SymmRuntime:
             return ALGO_TWOSHOT
         if o in ("nvls", "2") and self.multicast and need_mc:
             return ALGO_NVLS
-        # Measured on 8xB200 (profiles/allreduce_sweep_8gpu.json) and 2xB200: one-shot only wins
-        # in the pure-latency regime; above that the sliced kernels win at every size, and the
+        # Measured table (runtime/tuning.py; profiles/allreduce_sweep_*.json): one-shot only wins
+        # in the pure-latency regime; above it the sliced kernels win at every size and the
         # in-switch reduction (NVLS) beats P2P two-shot from ~64 KB up to 1 GB (838 vs 641 GB/s).
-        if nbytes <= (8 << 10):
-            return ALGO_ONESHOT
-        if self.world <= 2:
-            return ALGO_TWOSHOT
-        return ALGO_NVLS if (self.multicast and need_mc) else ALGO_TWOSHOT
+        from . import tuning
+        return tuning.choose(self.world, nbytes, bool(self.multicast and need_mc))
 
     def pick_blocks(self, algo: int, nbytes: int) -> int:
         work = nbytes if algo == ALGO_ONESHOT else nbytes // max(self.world, 1)
