@@ -230,11 +230,16 @@ class FusedEngine:
         """Materialise ``optimizer.state`` (torch layout) from the flat state arenas so
         ``state_dict()`` / checkpointing / ``broadcast_optimizer_state`` see the usual
         per-parameter entries.  State of sliced buckets is sharded across ranks; unowned
-        slices are still zero, so a Sum-allreduce of the arena reassembles it."""
-        if self.steps == 0:
+        slices are still zero, so a Sum-allreduce of the arena reassembles it — which makes
+        this call a COLLECTIVE when world > 1 (every rank must call it, like FSDP's full optimizer
+        state dict): ``sd = opt.state_dict()`` on all ranks, then ``if hvd.rank() == 0: save``."""
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
+        # the device-side counters are authoritative (CUDA-graph replays do not run Python)
+        steps_dev = int(self.step_ctr.max().item()) if self.step_ctr.numel() else 0
+        self.steps = max(self.steps, steps_dev)
+        if steps_dev == 0:
             return
         opt = self.opt
-        torch.cuda.current_stream(self.device).wait_stream(self.side)
         for b in self.buckets:
             ar = self.arenas[b.dtype]
             lo, hi = b.flat_offset, b.flat_offset + b.numel
@@ -251,7 +256,7 @@ class FusedEngine:
                     if opt.param_groups[b.group_index].get("momentum", 0.0) != 0.0:
                         st["momentum_buffer"] = v0
                 else:
-                    st["step"] = torch.tensor(float(self.steps))
+                    st["step"] = torch.tensor(float(steps_dev))
                     st["exp_avg"] = v0
                     st["exp_avg_sq"] = s1[s.offset: s.offset + s.numel].view(s.param.shape)
         self._state_dirty = False

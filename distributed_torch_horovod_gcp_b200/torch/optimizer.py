@@ -317,6 +317,23 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             tl.end("optimizer", "STEP")
 
     def _step_impl(self, closure=None):
+        if self._engine is not None and self._engine.fuses_update:
+            # The reduction kernels ARE the update.  step() therefore only has to make sure every
+            # bucket has been launched exactly once for this iteration and order the stream.
+            if not self._should_synchronize:
+                raise RuntimeError(
+                    "skip_synchronize() requires the un-fused path: construct "
+                    "DistributedOptimizer(..., fused=False) when gradients must be modified "
+                    "(e.g. clipped) between synchronize() and step().")
+            loss = None
+            if closure is not None:
+                with torch.enable_grad():
+                    loss = closure()
+            if not self._synchronized:        # an explicit synchronize() already applied the update
+                self.synchronize()
+            self._synchronized = False
+            self._engine.after_step()
+            return loss
         if self._should_synchronize:
             if self._synchronized:
                 warnings.warn("optimizer.step() called without optimizer.skip_synchronize() "
@@ -324,22 +341,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                               "slowdown. You may want to consider using "
                               "optimizer.skip_synchronize() context if you use "
                               "optimizer.synchronize() in your code.")
-            if self._engine is not None and self._engine.fuses_update:
-                # the update happens inside the bucket kernels; run closure first if any
-                loss = None
-                if closure is not None:
-                    with torch.enable_grad():
-                        loss = closure()
-                self.synchronize()
-                self._synchronized = False
-                self._engine.after_step()
-                return loss
             self.synchronize()
-        elif self._engine is not None and self._engine.fuses_update:
-            raise RuntimeError(
-                "skip_synchronize() requires the un-fused path: construct "
-                "DistributedOptimizer(..., fused=False) when gradients must be modified "
-                "(e.g. clipped) between synchronize() and step().")
         self._synchronized = False
         return super(self.__class__, self).step(closure)
 
@@ -369,10 +371,18 @@ class _DistributedOptimizer(torch.optim.Optimizer):
     def state_dict(self):
         """Same layout as the wrapped optimizer's ``state_dict()``.  With the fused engine the
         momentum / Adam moments live in flat fp32 arenas (sharded by slice for the two-shot/NVLS
-        buckets); they are gathered and exposed as ordinary per-parameter entries first, so
-        "rank 0 saves" checkpointing works unchanged."""
+        buckets); they are gathered and exposed as ordinary per-parameter entries first.  With
+        world > 1 this gather is a COLLECTIVE: call ``state_dict()`` on every rank, then let rank 0
+        write the file ("rank 0 saves, then broadcast on resume")."""
         if self._engine is not None:
-            self._engine.export_state()
+            from .mpi_ops import HorovodInternalError
+            try:
+                self._engine.export_state()
+            except HorovodInternalError as e:
+                raise HorovodInternalError(
+                    str(e) + "  [optimizer.state_dict() is a collective when the fused engine "
+                    "shards optimizer state across ranks: call it on EVERY rank, then save on "
+                    "rank 0]") from e
         return super(self.__class__, self).state_dict()
 
     def load_state_dict(self, state_dict):
