@@ -264,3 +264,58 @@ def timeline_and_elastic(hvd, tmpdir):
     st.sync()
     assert st.epoch == 7
     return True
+
+
+def optimizer_options(hvd):
+    """groups / num_groups / compression / gradient_predivide_factor / op=Sum through the bucket path."""
+    world, rank = hvd.size(), hvd.rank()
+    torch.manual_seed(11)
+    X, Y = torch.randn(4 * world, 6), torch.randn(4 * world, 3)
+    xs, ys = X[rank * 4:(rank + 1) * 4], Y[rank * 4:(rank + 1) * 4]
+
+    def run(**kw):
+        m = _model(0)
+        lr = kw.pop("lr", 0.1)
+        opt = hvd.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=lr),
+                                       named_parameters=m.named_parameters(), **kw)
+        hvd.broadcast_parameters(m.state_dict(), 0)
+        F.mse_loss(m(xs), ys).backward()
+        opt.step()
+        opt.zero_grad()
+        return m, opt
+
+    ref = _model(0)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.1)
+    F.mse_loss(ref(X), Y).backward()
+    ropt.step()
+    want = [p.detach().clone() for p in ref.parameters()]
+
+    m, opt = run(num_groups=2)
+    assert len(opt.bucket_plan()) >= 2
+    for a, b in zip(m.parameters(), want):
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
+    mg = _model(0)
+    ps = list(mg.parameters())
+    m, opt = run(gradient_predivide_factor=2.0)
+    for a, b in zip(m.parameters(), want):
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
+    m, opt = run(compression=hvd.Compression.fp16)
+    for a, b in zip(m.parameters(), want):
+        torch.testing.assert_close(a, b, rtol=2e-3, atol=2e-3)
+    # op=Sum with lr/world == Average with lr
+    m, opt = run(op=hvd.Sum, lr=0.1 / world)
+    for a, b in zip(m.parameters(), want):
+        torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6)
+    # explicit groups: first two params share a bucket, the rest are planned automatically
+    m = _model(0)
+    ps = list(m.parameters())
+    opt = hvd.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1),
+                                   named_parameters=m.named_parameters(), groups=[[ps[0], ps[1]]])
+    plan = opt.bucket_plan()
+    assert {s.name for s in plan[0].slots} == {"0.weight", "0.bias"} and len(plan) == 2
+    try:
+        hvd.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1), num_groups=2, groups=[[ps[0]]])
+        raise RuntimeError("num_groups+groups should raise")
+    except ValueError:
+        pass
+    return True

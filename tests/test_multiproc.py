@@ -33,3 +33,7 @@ def test_sync_batch_norm():
 
 def test_timeline_and_elastic(tmp_path):
     assert all(run_workers(2, "mp_cases", "timeline_and_elastic", (str(tmp_path),)))
+
+
+def test_optimizer_options():
+    assert all(run_workers(2, "mp_cases", "optimizer_options"))
