@@ -86,3 +86,31 @@ def test_cli_errors():
     r = subprocess.run([os.path.join(ROOT, "bin", "horovodrun"), "-np", "1", "echo", "hi"],
                        capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and r.stdout.strip() == "hi"
+
+
+def test_remote_hosts_via_ssh_and_output_files(tmp_path):
+    """Non-local hosts are reached over `ssh host 'cd <cwd> && env K=V... cmd'` (a fake ssh on PATH
+    executes the remote command locally); --output-filename writes per-rank logs."""
+    fake = tmp_path / "bin"
+    fake.mkdir()
+    ssh = fake / "ssh"
+    ssh.write_text("#!/usr/bin/env bash\n"
+                   "# fake ssh: drop options, first non-option arg is the host, the rest is the command\n"
+                   "while [[ \"$1\" == -* ]]; do if [[ \"$1\" == -o || \"$1\" == -p || \"$1\" == -i ]]; then shift; fi; shift; done\n"
+                   "host=\"$1\"; shift\n"
+                   "echo \"ssh-to:$host\" >&2\n"
+                   "exec bash -c \"$*\"\n")
+    ssh.chmod(0o755)
+    env = dict(os.environ, PYTHONPATH=ROOT, PATH=f"{fake}:{os.environ['PATH']}")
+    code = "import os;print('R',os.environ['RANK'],os.environ['HOROVOD_HOSTNAME'],os.environ['HOROVOD_CROSS_RANK'],os.environ['MASTER_ADDR'])"
+    out_dir = tmp_path / "logs"
+    r = subprocess.run(HRUN + ["-np", "3", "-H", "nodeA:2,nodeB:2", "-p", "2222", "--output-filename",
+                               str(out_dir), sys.executable, "-c", code],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = sorted(l for l in r.stdout.splitlines() if "R " in l)
+    assert lines == ["[0]<stdout>:R 0 nodeA 0 nodeA", "[1]<stdout>:R 1 nodeA 0 nodeA",
+                     "[2]<stdout>:R 2 nodeB 1 nodeA"]
+    assert r.stderr.count("ssh-to:nodeA") == 2 and r.stderr.count("ssh-to:nodeB") == 1
+    for rank in range(3):
+        assert (out_dir / f"rank.{rank}" / "stdout").read_text().startswith(f"R {rank}")
