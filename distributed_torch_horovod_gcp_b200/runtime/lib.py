@@ -33,6 +33,16 @@ def _load(name: str) -> Optional[ctypes.CDLL]:
         return _cache[name]
     p = _path(name)
     lib = None
+    if not os.path.exists(p) and os.environ.get("B200DP_NO_AUTOBUILD", "0") != "1":
+        # fresh checkout (the .so files are git-ignored): build in-tree once, if nvcc is present
+        try:
+            import torch
+            if torch.cuda.is_available():
+                from .. import build as _build
+                _build.build()
+        except Exception as e:  # noqa: BLE001 - reported below if the library is still missing
+            import warnings
+            warnings.warn(f"[b200dp] in-tree native build failed: {e}")
     if os.path.exists(p):
         lib = ctypes.CDLL(p, mode=ctypes.RTLD_GLOBAL)
     else:
