@@ -52,7 +52,19 @@ def _digest(paths: List[str], flags: List[str]) -> str:
 
 
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> List[str]:
+    """Build (or re-use) the in-tree libraries.  Serialised across processes with a file lock so
+    that N ranks starting on a fresh checkout do not run nvcc into the same output file."""
+    import fcntl
     os.makedirs(LIB, exist_ok=True)
+    with open(os.path.join(LIB, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose, ptxas_info)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool, ptxas_info: bool) -> List[str]:
     built = []
     nvcc = _nvcc()
     for name, srcs in TARGETS.items():
