@@ -582,6 +582,32 @@ int grid_for(long long nvec, int V) {
   return (int)blocks;
 }
 
+// fp32 split-K workspace -> gradient tensor: dst (bf16 or fp32) = (accumulate ? dst : 0) + src, and the
+// workspace is re-zeroed in the same pass so the next step's RED.ADDs start from zero without a memset.
+template <bool OUT_BF16>
+__global__ void cast_acc_zero_kernel(float* __restrict__ src, void* __restrict__ dst, long long n4,
+                                     int accumulate, int zero_src) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = reinterpret_cast<float4*>(src)[i];
+    if (zero_src) reinterpret_cast<float4*>(src)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (OUT_BF16) {
+      uint2* d = reinterpret_cast<uint2*>(dst) + i;
+      if (accumulate) {
+        const uint2 o = *d;
+        v.x += __uint_as_float(o.x << 16); v.y += __uint_as_float(o.x & 0xffff0000u);
+        v.z += __uint_as_float(o.y << 16); v.w += __uint_as_float(o.y & 0xffff0000u);
+      }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      *d = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    } else {
+      float4* d = reinterpret_cast<float4*>(dst) + i;
+      if (accumulate) { const float4 o = *d; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      *d = v;
+    }
+  }
+}
+
 bool shape_ok(int C) {
   const int V = C / 8;
   return C % 8 == 0 && V >= 1 && V <= THREADS && (THREADS % V) == 0;   // V | 256 | 1024
@@ -592,6 +618,25 @@ bool shape_ok(int C) {
 extern "C" {
 
 const char* b200dp_ew_last_error() { return g_err; }
+
+// dst[n] (bf16 if out_bf16 else fp32) (+)= src[n] (fp32); optionally re-zero src.  n % 4 == 0.
+int b200dp_cast_acc_zero(void* src, void* dst, long long n, int out_bf16, int accumulate, int zero_src,
+                         unsigned long long stream) {
+  if (n % 4) {
+    snprintf(g_err, sizeof(g_err), "cast_acc_zero: n must be a multiple of 4");
+    return -1;
+  }
+  const long long n4 = n / 4;
+  int grid = (int)((n4 + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  if (out_bf16) cast_acc_zero_kernel<true><<<grid, 256, 0, st>>>((float*)src, dst, n4, accumulate, zero_src);
+  else cast_acc_zero_kernel<false><<<grid, 256, 0, st>>>((float*)src, dst, n4, accumulate, zero_src);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("cast_acc_zero launch", e);
+  return 0;
+}
 
 int b200dp_bn_supported(int C) { return shape_ok(C) ? 1 : 0; }
 

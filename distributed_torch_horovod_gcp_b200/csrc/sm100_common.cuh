@@ -1,0 +1,364 @@
+// Shared sm_100a device helpers: mbarrier / TMA / tcgen05 PTX wrappers, UMMA descriptors and the
+// fused TMEM->register->smem->TMA-store epilogue used by the GEMM (gemm_sm100.cu), the implicit-GEMM
+// convolution (conv_sm100.cu) and the attention kernels (attn_sm100.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;          // 64 bf16 = 128 bytes = one 128B swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 320;     // 10 warps: TMA, MMA, 8 epilogue (2 per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
+
+struct GemmParams {
+  int M, N, K;
+  int ldc;                 // elements
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int splits;              // split-K factor (>=1)
+  int act;                 // 0 none, 1 relu, 2 gelu(erf), 3 *gelu'(aux), 4 *(aux>0)  [aux = residual ptr]
+  int out_mode;            // 0: bf16 store, 1: fp32 atomic add (split-K / accumulate), 2: fp32 store
+  void* C;
+  const void* bias;        // bf16 [N] or nullptr
+  const void* bias_f32;    // fp32 [N] or nullptr
+  const void* residual;    // bf16 [M, ldc] or nullptr (added after act; or `aux` for act 3/4)
+  void* preact;            // optional bf16 [M, ldc]: pre-activation values (saved for backward)
+  int tma_store;           // out_mode 0: stage the tile in swizzled smem and write it with TMA bulk stores
+  int n_fastest;           // tile order: consecutive CTAs walk the N blocks of one M block first (A tile is
+                           // fetched from HBM once and re-used from L2 while the whole B matrix stays in L2)
+  float alpha;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait suspends for a bounded time per attempt; a %globaltimer watchdog (4 s) turns a protocol
+  // bug (lost arrive / wrong phase) into a trap ("unspecified launch failure") instead of a GPU hang.
+  uint32_t done = 0;
+  unsigned long long t0 = 0;
+  for (uint32_t tries = 0; !done; ++tries) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && (tries & 1023u) == 1023u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// 4D tiled loads/stores (NHWC activations as {C, W, H, N} tensors): out-of-bounds box elements — negative
+// or past-the-end coordinates, i.e. the convolution's zero padding — are zero-filled on load and skipped
+// on store by the TMA unit itself.
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+      "[%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 64-bit UMMA shared-memory descriptor (sm_100: version=1), 128B swizzle.
+//   K-major  : rows of 128 B (64 bf16 of K), 8-row groups 1024 B apart (SBO); LBO unused (=1).
+//   MN-major : [k rows][64 mn elements] atoms of 128 B rows; 8-row k-groups SBO=1024 B apart,
+//              64-element mn chunks LBO bytes apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                              uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // LayoutType::SWIZZLE_128B
+  return d;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // D format: F32
+  d |= 1u << 7;                      // A format: BF16
+  d |= 1u << 10;                     // B format: BF16
+  d |= (A_MN ? 1u : 0u) << 15;       // A major
+  d |= (B_MN ? 1u : 0u) << 16;       // B major
+  d |= (uint32_t)(BN >> 3) << 17;    // N
+  d |= (uint32_t)(BLOCK_M >> 4) << 24;  // M
+  return d;
+}
+
+// erf via Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7, far below bf16 resolution): 1 rcp + 1 ex2 + 6 fma
+// instead of the ~40-instruction erff — the epilogue, not the MMA, bounds the GELU GEMMs.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float y = 1.0f - poly * t * __expf(-ax * ax);
+  return copysignf(y, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
+}
+
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + fast_erf(x * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& x, float* f) {
+  const uint32_t wv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    f[2 * t] = __uint_as_float(wv[t] << 16);
+    f[2 * t + 1] = __uint_as_float(wv[t] & 0xffff0000u);
+  }
+}
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint32_t wv[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * t], v[2 * t + 1]);
+    wv[t] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(wv[0], wv[1], wv[2], wv[3]);
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 3 : ((BN == 128) ? 5 : 6);
+  static constexpr int TMEM_COLS = 2 * BN;       // double-buffered fp32 accumulator
+  static constexpr int STORE_BYTES = EPI_WARPS * 2 * 4096;   // per epilogue warp: out + preact staging (32 rows x 128 B each)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// Epilogue of one 32-row slab (this warp's TMEM lane quarter) of a 128 x BN accumulator: TMEM ->
+// registers -> alpha/bias/activation/residual -> bf16 via swizzled smem + TMA bulk store, or fp32
+// store / atomic add.  Shared by the 1-CTA and the 2-CTA (cta_group::2) kernels.
+// Where a 32-row slab goes.  rank4 == 0: rows m_row0.. of the row-major [M, ldc] matrix (2D map).
+// rank4 == 1 (convolution): the slab is the {64 c, sw, sh, sn} sub-box at pixel (w, h, n) of an NHWC
+// tensor; c_ptr/ld override p.C/p.ldc for the fp32 modes (per-tap column offset of the wgrad output).
+struct StoreAt {
+  int rank4, w, h, n;
+  void* c_ptr;
+};
+
+template <int BN>
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtensorMap* map_c,
+                                              const CUtensorMap* map_z, uint32_t tmem_base, int acc, int q,
+                                              int lane, int m_row0, int n_idx, int c_begin, int c_end,
+                                              uint8_t* my_store, const StoreAt at = StoreAt{0, 0, 0, 0, nullptr}) {
+  const int row = m_row0 + lane;
+  const bool row_ok = row < p.M;
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 64) {
+    // two x32 loads in flight before the wait: 64 accumulator columns of this lane's row
+    uint32_t r[64];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+    tc_ld_32x32b_x32(taddr, r);
+    tc_ld_32x32b_x32(taddr + 32, r + 32);
+    tc_wait_ld();
+    const int col0 = n_idx + c0;
+    if (col0 >= p.N) continue;                       // warp-uniform
+    const int ncols = min(64, p.N - col0);           // N % 8 == 0 is enforced by the host
+    float v[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+    // NOTE: everything in this block that is warp-collective (__syncwarp, staging) must be reached by
+    // all 32 lanes, so only the per-row global accesses are predicated on row_ok.
+    if (p.out_mode != 1) {
+      if (p.bias != nullptr) {
+        const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i < ncols) v[i] += __bfloat162float(b[i]);
+      } else if (p.bias_f32 != nullptr) {
+        const float* b = reinterpret_cast<const float*>(p.bias_f32) + col0;
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i < ncols) v[i] += b[i];
+      }
+      if (p.preact != nullptr && !(p.out_mode == 0 && p.tma_store) && row_ok) {
+        uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.preact) +
+                                             (size_t)row * p.ldc + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j * 8 < ncols) pp[j] = pack8(v + j * 8);
+      }
+      if (p.preact != nullptr && p.out_mode == 0 && p.tma_store) {
+        // pre-activation tile -> second staging buffer (stored by TMA together with the output)
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(my_store + 4096 + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8(v + j * 8);
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.0f);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = gelu_erf(v[i]);
+      }
+      if (p.residual != nullptr && row_ok) {
+        const uint4* rp = reinterpret_cast<const uint4*>(
+            reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldc + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j * 8 < ncols) {
+            float a[8];
+            unpack8(rp[j], a);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              if (p.act == 3) v[j * 8 + t] *= gelu_erf_grad(a[t]);
+              else if (p.act == 4) v[j * 8 + t] = a[t] > 0.0f ? v[j * 8 + t] : 0.0f;
+              else v[j * 8 + t] += a[t];
+            }
+          }
+        }
+      }
+    }
+    if (p.out_mode == 0 && p.tma_store) {
+      // stage 32 rows x 128 B in the 128B-swizzled layout (conflict-free 16 B stores), then one
+      // lane issues a bulk tensor store; TMA clips rows >= M and columns >= N.
+      uint8_t* buf = my_store;
+      if (lane == 0) tma_store_wait_read<0>();           // previous chunk's bulk stores have read the staging
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8(v + j * 8);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if (at.rank4) {
+          tma_store_4d(map_c, buf, col0, at.w, at.h, at.n);
+        } else {
+          tma_store_2d(map_c, buf, col0, m_row0);
+          if (p.preact != nullptr) tma_store_2d(map_z, buf + 4096, col0, m_row0);
+        }
+        tma_store_commit();
+      }
+    } else if (row_ok) {
+      if (p.out_mode == 0) {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) +
+                                              (size_t)row * p.ldc + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j * 8 < ncols) dst[j] = pack8(v + j * 8);
+      } else {
+        float* dst = reinterpret_cast<float*>(at.c_ptr ? at.c_ptr : p.C) + (size_t)row * p.ldc + col0;
+        if (p.out_mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j * 4 < ncols)
+              reinterpret_cast<float4*>(dst)[j] =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i < ncols) atomicAdd(dst + i, v[i]);     // RED.ADD.F32 (split-K accumulation)
+        }
+      }
+    }
+  }
+}
+
+}  // namespace

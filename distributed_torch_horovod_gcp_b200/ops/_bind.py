@@ -8,6 +8,8 @@ from . import gemm as _gemm
 from . import bn as _bn
 from . import lstm_fused as _lstm
 from . import ln as _ln
+from . import conv as _conv
+from .conv import conv3x3, conv2d as conv2d_implicit  # noqa: F401
 from .ln import layer_norm  # noqa: F401
 from .gemm import linear, mlp, qkv_proj  # noqa: F401  (re-exported as kernels.linear / .mlp / .qkv_proj)
 from .bn import conv_bn_act, bn_act, max_pool_3x3_s2  # noqa: F401
@@ -18,6 +20,7 @@ def register(lib, have: Dict[str, bool]) -> None:
     _bn.register(lib, have)
     _lstm.register(lib, have)
     _ln.register(lib, have)
+    _conv.register(lib, have)
 
 
 def linear_supported(x, weight) -> bool:

@@ -1,6 +1,8 @@
 """Fused NHWC BatchNorm(+residual)(+ReLU) (csrc/elementwise.cu) and the conv+BN+act unit used by
 the ResNet blocks.  1x1 stride-1 convolutions run on the tcgen05 GEMM (an NHWC activation is a
-row-major [N*H*W, C] matrix); other convolutions use cuDNN until the implicit-GEMM kernel lands."""
+row-major [N*H*W, C] matrix), the 7x7 stem on im2col + that GEMM, and 3x3 / strided 1x1 convolutions
+on the implicit-GEMM kernel (ops/conv.py, csrc/conv_sm100.cu); cuDNN is only the fallback for shapes
+none of these cover (e.g. a 3-channel 3x3 stem)."""
 from __future__ import annotations
 
 import ctypes
@@ -200,6 +202,9 @@ def conv2d(x, conv: torch.nn.Conv2d):
         return y2.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2)      # logical NCHW, NHWC memory
     if _is_stem_conv(x, conv):
         return _StemConvFn.apply(x, w)
+    from . import conv as _conv
+    if conv.bias is None and _conv.supported(x, w, conv.stride, conv.padding, conv.dilation, conv.groups):
+        return _conv.conv2d(x, w, conv.stride[0], conv.padding[0])
     return F.conv2d(x, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
