@@ -294,6 +294,7 @@ int fail(const char* msg, int code = 0) {
 }
 
 int ensure_init() {
+  bind_primary_context();
   if (g_encode) return 0;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult st;
@@ -583,7 +584,7 @@ int b200dp_conv_wgrad(const void* dy, const void* x, void* dw_acc, int N, int H,
     }
   const int tiles = p.g.num_m_blocks * p.g.num_n_blocks * R * S;
   if (splits <= 0) {
-    splits = (2 * g_num_sms + tiles - 1) / tiles;        // ~2 work items per SM
+    splits = (g_num_sms + tiles - 1) / tiles;            // one wave: every extra split costs a tile of REDs
     const int max_splits = kblocks / 8 > 1 ? kblocks / 8 : 1;
     if (splits > max_splits) splits = max_splits;
   }

@@ -440,6 +440,7 @@ int fail(const char* msg, int code = 0) {
 }
 
 int ensure_init() {
+  bind_primary_context();
   if (g_encode) return 0;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult st;

@@ -351,13 +351,45 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
             if (j * 4 < ncols)
               reinterpret_cast<float4*>(dst)[j] =
                   make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i < ncols) atomicAdd(dst + i, v[i]);     // RED.ADD.F32 (split-K accumulation)
         }
       }
     }
+    if (p.out_mode == 1) {
+      // split-K accumulation: transpose the 32 x 64 fp32 slab through the (8 KB) staging buffer so that a
+      // warp-level RED covers two 256-byte row segments with 16-byte vectors (red.global.add.v4.f32)
+      // instead of 32 scattered 4-byte atomics per instruction.
+      float* stage = reinterpret_cast<float*>(my_store);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        *reinterpret_cast<float4*>(stage + lane * 64 + ((j ^ (lane & 15)) << 2)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      __syncwarp();
+      float* cbase = reinterpret_cast<float*>(at.c_ptr ? at.c_ptr : p.C);
+      const int ch = lane & 15;
+#pragma unroll 4
+      for (int it = 0; it < 16; ++it) {
+        const int rr = it * 2 + (lane >> 4);
+        const float4 t = *reinterpret_cast<const float4*>(stage + rr * 64 + ((ch ^ (rr & 15)) << 2));
+        if (m_row0 + rr < p.M && ch * 4 < ncols) {
+          float* dst = cbase + (size_t)(m_row0 + rr) * p.ldc + col0 + ch * 4;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z),
+                       "f"(t.w)
+                       : "memory");
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// cuTensorMapEncode* is a driver-API call: it fails with CUDA_ERROR_INVALID_CONTEXT on a thread that
+// has not yet bound the primary context (e.g. an autograd worker whose first GPU op is one of ours).
+inline void bind_primary_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
   }
 }
 

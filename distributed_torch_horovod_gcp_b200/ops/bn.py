@@ -14,6 +14,7 @@ import torch.nn.functional as F
 
 from . import counters
 from . import gemm as _gemm
+from . import grad_sink
 
 _lib = None
 _USE_GEMM_1X1 = os.environ.get("B200DP_CONV1X1_GEMM", "1") == "1"
@@ -84,6 +85,11 @@ class _BNActFn(torch.autograd.Function):
         counters.bump("bn_fwd", 2 if stats_in is not None else 3)
         ctx.save_for_backward(x, mask, mean, invstd, a)
         ctx.relu, ctx.has_res, ctx.pdtype = relu, residual is not None, gamma.dtype
+        ctx.affine = (gamma, beta)
+        if ctx.needs_input_grad[1]:
+            grad_sink.note_forward(gamma)
+        if ctx.needs_input_grad[2]:
+            grad_sink.note_forward(beta)
         return y
 
     @staticmethod
@@ -97,15 +103,29 @@ class _BNActFn(torch.autograd.Function):
         dres = torch.empty_like(x, memory_format=torch.channels_last) if (ctx.has_res and ctx.relu) \
             else None
         sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
-        dgb = torch.empty(2 * C, dtype=ctx.pdtype, device=x.device)
+        # dgamma / dbeta: straight into the gradient-bucket slots when both parameters offer a sink
+        gamma, beta = ctx.affine
+        gd, ga, gdone = grad_sink.begin(gamma)
+        bd, ba, bdone = grad_sink.begin(beta)
+        direct = gd is not None and bd is not None and not ga and not ba
+        if direct:
+            dg_ptr, db_ptr = gd.data_ptr(), bd.data_ptr()
+        else:
+            dgb = torch.empty(2 * C, dtype=ctx.pdtype, device=x.device)
+            dg_ptr, db_ptr = dgb.data_ptr(), dgb.data_ptr() + C * dgb.element_size()
         st = torch.cuda.current_stream(x.device).cuda_stream
         _ck(_lib.b200dp_bn_bwd(dy.data_ptr(), x.data_ptr(), mask.data_ptr() if mask is not None else None,
                                dx.data_ptr(), dres.data_ptr() if dres is not None else None,
                                a.data_ptr(), mean.data_ptr(), invstd.data_ptr(), sums.data_ptr(),
-                               dgb.data_ptr(), dgb.data_ptr() + C * dgb.element_size(),
+                               dg_ptr, db_ptr,
                                int(ctx.pdtype == torch.bfloat16), M, C, int(ctx.relu), st))
         counters.bump("bn_bwd", 2)
-        dgamma, dbeta = dgb[:C], dgb[C:]                  # written by the kernel in the param dtype
+        if direct:
+            dgamma = dbeta = None
+            gdone()
+            bdone()
+        else:
+            dgamma, dbeta = dgb[:C], dgb[C:]              # written by the kernel in the param dtype
         if ctx.has_res and dres is None:
             dres = dy                       # no ReLU: the residual branch gets dy unchanged
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None
@@ -198,7 +218,7 @@ def conv2d(x, conv: torch.nn.Conv2d):
     if _is_gemm_conv(x, conv):
         N, C, H, W = x.shape
         x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, C)             # view: NHWC rows
-        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C))              # [M, Cout]
+        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C), owner=w)     # [M, Cout]
         return y2.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2)      # logical NCHW, NHWC memory
     if _is_stem_conv(x, conv):
         return _StemConvFn.apply(x, w)

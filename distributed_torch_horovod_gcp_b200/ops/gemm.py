@@ -18,6 +18,7 @@ from typing import Optional
 import torch
 
 from . import counters
+from . import grad_sink
 
 _lib = None
 ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}
@@ -33,6 +34,8 @@ def register(lib, have):
                                      i, i, i, ctypes.c_uint64]
     lib.b200dp_gemm_bf16.restype = i
     lib.b200dp_gemm_last_error.restype = ctypes.c_char_p
+    if hasattr(lib, "b200dp_cast_acc_zero"):
+        lib.b200dp_cast_acc_zero.argtypes = [vp, vp, ctypes.c_longlong, i, i, i, ctypes.c_uint64]
     have["gemm"] = True
     have["linear"] = True
 
@@ -105,16 +108,53 @@ def _ones(M: int, device) -> torch.Tensor:
     return t
 
 
-def wgrad(dz: torch.Tensor, x2: torch.Tensor, N: int, K: int, M: int, dtype) -> torch.Tensor:
-    """dW[N,K] = dz[M,N]^T @ x2[M,K] with both operands MN-major (no transposes)."""
+_ws_cache = {}
+
+
+def _workspace(key, numel: int, device) -> torch.Tensor:
+    """fp32 split-K accumulator, zero on entry: ``b200dp_cast_acc_zero`` re-zeroes it while converting,
+    so no per-step memset / allocation is needed."""
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() != numel:
+        ws = torch.zeros(numel, dtype=torch.float32, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def wgrad(dz: torch.Tensor, x2: torch.Tensor, N: int, K: int, M: int, dtype, owner=None):
+    """dW[N,K] = dz[M,N]^T @ x2[M,K] with both operands MN-major (no transposes).  With ``owner`` (the
+    parameter) carrying a grad sink the result goes straight into its gradient-bucket slot and
+    ``None`` is returned (ops/grad_sink.py)."""
+    dst, acc, done = grad_sink.begin(owner) if owner is not None else (None, False, None)
+    if dst is not None and dst.dtype != dtype:
+        dst, acc, done = None, False, None
+    out = dst.as_strided((N, K), (K, 1)) if dst is not None else None
     splits = _splits_for(N, K, M)
     if splits == 1 and dtype == torch.bfloat16:
-        dw = torch.empty((N, K), dtype=torch.bfloat16, device=dz.device)
-        gemm(dz, x2, dw, N, K, M, a_mn=True, b_mn=True)              # TMA-store epilogue, bf16
-        return dw
-    acc = torch.zeros((N, K), dtype=torch.float32, device=dz.device)
-    gemm(dz, x2, acc, N, K, M, a_mn=True, b_mn=True, out_mode=1, splits=splits)
-    return acc.to(dtype)
+        dw = out if out is not None else torch.empty((N, K), dtype=torch.bfloat16, device=dz.device)
+        gemm(dz, x2, dw, N, K, M, a_mn=True, b_mn=True, residual=dw if acc else None)
+    else:
+        key = (owner.data_ptr() if owner is not None else 0, N, K, dz.device.index)
+        if owner is None or (N * K) % 4 or not hasattr(_lib, "b200dp_cast_acc_zero"):
+            accum = torch.zeros((N, K), dtype=torch.float32, device=dz.device)
+            gemm(dz, x2, accum, N, K, M, a_mn=True, b_mn=True, out_mode=1, splits=splits)
+            dw = accum.to(dtype)
+            if out is not None:
+                out.add_(dw) if acc else out.copy_(dw)
+        else:
+            ws = _workspace(key, N * K, dz.device).view(N, K)
+            gemm(dz, x2, ws, N, K, M, a_mn=True, b_mn=True, out_mode=1, splits=splits)
+            dw = out if out is not None else torch.empty((N, K), dtype=dtype, device=dz.device)
+            rc = _lib.b200dp_cast_acc_zero(ws.data_ptr(), dw.data_ptr(), N * K, int(dtype == torch.bfloat16),
+                                           int(acc and out is not None), 1,
+                                           torch.cuda.current_stream(dz.device).cuda_stream)
+            if rc != 0:
+                raise RuntimeError("cast_acc_zero failed")
+            counters.bump("cast_acc_zero")
+    if done is not None:
+        done()
+        return None
+    return dw
 
 
 def bias_grad(dz: torch.Tensor, N: int, M: int, dtype) -> torch.Tensor:
@@ -128,8 +168,11 @@ def bias_grad(dz: torch.Tensor, N: int, M: int, dtype) -> torch.Tensor:
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, act, residual):
+    def forward(ctx, x, weight, bias, act, residual, owner=None):
         K = weight.shape[1]
+        ctx.owner = owner if owner is not None else weight
+        if ctx.needs_input_grad[1]:
+            grad_sink.note_forward(ctx.owner)
         N = weight.shape[0]
         x2 = x.reshape(-1, K)
         if x2.stride(-1) != 1 or (x2.stride(0) % 8) or (x2.data_ptr() % 16):
@@ -169,10 +212,10 @@ class _LinearFn(torch.autograd.Function):
             gemm(dz, weight, dx, M, K, N, b_mn=True)                       # dx = dz @ W
             dx = dx.view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
-            dw = wgrad(dz, x2, N, K, M, weight.dtype)                      # dW = dz^T @ x
+            dw = wgrad(dz, x2, N, K, M, weight.dtype, owner=ctx.owner)     # dW = dz^T @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = bias_grad(dz, N, M, ctx.bias_dtype)
-        return dx, dw, db, None, dres
+        return dx, dw, db, None, dres, None
 
 
 def act_backward(dy2: torch.Tensor, z: torch.Tensor, act: int) -> torch.Tensor:
@@ -206,6 +249,11 @@ class _MLPFn(torch.autograd.Function):
             r2 = r2.contiguous()
         gemm(h, w2, out, M, w2.shape[0], Hd, bias=b2, residual=r2)
         ctx.save_for_backward(x2, w1, w2, z, h)
+        ctx.owners = (w1, w2)
+        if ctx.needs_input_grad[1]:
+            grad_sink.note_forward(w1)
+        if ctx.needs_input_grad[3]:
+            grad_sink.note_forward(w2)
         ctx.x_shape, ctx.has_res = x.shape, residual is not None
         ctx.bdt = (b1.dtype, b2.dtype)
         return out.view(*x.shape[:-1], w2.shape[0])
@@ -221,9 +269,9 @@ class _MLPFn(torch.autograd.Function):
         dev = dy.device
         dz = torch.empty((M, Hd), dtype=torch.bfloat16, device=dev)
         gemm(dy2, w2, dz, M, Hd, Do, b_mn=True, residual=z, act=3)        # (dy @ W2) * gelu'(z)
-        dw2 = wgrad(dy2, h, Do, Hd, M, w2.dtype)
+        dw2 = wgrad(dy2, h, Do, Hd, M, w2.dtype, owner=ctx.owners[1])
         db2 = bias_grad(dy2, Do, M, ctx.bdt[1])
-        dw1 = wgrad(dz, x2, Hd, D, M, w1.dtype)
+        dw1 = wgrad(dz, x2, Hd, D, M, w1.dtype, owner=ctx.owners[0])
         db1 = bias_grad(dz, Hd, M, ctx.bdt[0])
         dx = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
         gemm(dz, w1, dx, M, D, Hd, b_mn=True)
@@ -296,5 +344,7 @@ def qkv_proj(x, weight, bias):
     return _QKVFn.apply(x, weight, bias)
 
 
-def linear(x, weight, bias=None, act: Optional[str] = None, residual=None):
-    return _LinearFn.apply(x, weight, bias, ACT[act], residual)
+def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, owner=None):
+    """``owner``: the parameter whose storage ``weight`` is a 2D view of (a 1x1 conv weight), so the
+    weight gradient can be written into its gradient-bucket slot directly."""
+    return _LinearFn.apply(x, weight, bias, ACT[act], residual, owner)

@@ -35,6 +35,18 @@ def live_engines():
     return list(_ENGINES)
 
 
+def arena_view(flat: torch.Tensor, lo: int, param: torch.Tensor) -> torch.Tensor:
+    """View of ``flat[lo: lo + numel]`` with the parameter's shape AND memory layout: a channels_last
+    conv weight stays [Cout][R][S][Cin] inside the arena (it is the B operand of the implicit-GEMM
+    convolution as stored — ops/conv.py), everything else is plain row-major."""
+    n = param.numel()
+    seg = flat[lo: lo + n]
+    if param.dim() == 4 and not param.is_contiguous() and \
+            param.is_contiguous(memory_format=torch.channels_last):
+        return seg.as_strided(param.shape, param.stride())
+    return seg.view(param.shape)
+
+
 def _classify(opt) -> Optional[str]:
     """Return 'sgd' | 'adam' | 'adamw' if the wrapped optimizer's update rule is one the fused
     epilogue implements exactly, else None."""
@@ -107,14 +119,7 @@ class FusedEngine:
             for b in buckets:
                 ar = self.arenas[b.dtype]
                 for s in b.slots:
-                    lo = b.flat_offset + s.offset
-                    pv = ar["p"][lo: lo + s.numel].view(s.param.shape)
-                    pv.copy_(s.param.data)
-                    s.param.data = pv
-                    gv = ar["g"][lo: lo + s.numel].view(s.param.shape)
-                    if s.param.grad is not None:
-                        gv.copy_(s.param.grad)
-                    s.param.grad = gv
+                    self._rehome(ar, b, s, first=True)
         self.params_changed()
         nb = len(buckets)
         self.step_ctr = torch.zeros(nb, dtype=torch.int32, device=self.device)
@@ -127,12 +132,56 @@ class FusedEngine:
             self._args[b.index], self._algo[b.index] = self._make_args(b)
         self._done = torch.cuda.Event()
         self.steps = 0
+        self.rehomed = 0
         self.kernel_launches = 0
         self._state_dirty = False
         torch.cuda.synchronize(self.device)
         if self.world > 1:
             dist.barrier(group=_state.runtime().cpu_group)
         _ENGINES.add(self)
+
+    def _rehome(self, ar, b: Bucket, s, first: bool = False) -> bool:
+        """Make ``param.data`` / ``param.grad`` alias their arena slots.  Returns True if anything
+        had to be moved.  Called once at construction and re-checked at every bucket launch: code
+        that runs AFTER the optimizer is wrapped can silently re-point parameter storage —
+        ``model.to(device)`` on an ``nn.LSTM`` calls ``flatten_parameters()``, which ``set_()``s every
+        weight into a fresh cuDNN buffer (reference order: app/torch_train.py:259 then :261) — and
+        the kernels would then train the arena while the model reads the stale buffer."""
+        lo = b.flat_offset + s.offset
+        p = s.param
+        es = p.element_size()
+        moved = False
+        want_p = ar["p"].data_ptr() + lo * es
+        if first or p.data_ptr() != want_p:
+            pv = arena_view(ar["p"], lo, p)
+            pv.copy_(p.data)
+            p.data = pv
+            if ar["M"] is not None and not first:
+                ar["M"][lo: lo + s.numel].copy_(ar["p"][lo: lo + s.numel])
+            moved = True
+        g = p.grad
+        want_g = ar["g"].data_ptr() + lo * es
+        if first or g is None or g.data_ptr() != want_g:
+            gv = arena_view(ar["g"], lo, p)
+            if g is not None:
+                gv.copy_(g)
+            elif not first:
+                gv.zero_()
+            p.grad = gv
+            moved = True
+        return moved
+
+    def _check_homes(self, b: Bucket):
+        ar = self.arenas[b.dtype]
+        base_p, base_g = ar["p"].data_ptr(), ar["g"].data_ptr()
+        es = ar["p"].element_size()
+        for s in b.slots:
+            off = (b.flat_offset + s.offset) * es
+            g = s.param.grad
+            if s.param.data_ptr() != base_p + off or g is None or g.data_ptr() != base_g + off:
+                with torch.no_grad():
+                    self._rehome(ar, b, s)
+                self.rehomed += 1
 
     def _make_args(self, b: Bucket):
         S, symm = self.S, self.symm
@@ -182,6 +231,7 @@ class FusedEngine:
 
     def launch(self, b: Bucket):
         """Called from the autograd hook when the last gradient of ``b`` has been produced."""
+        self._check_homes(b)
         a = self._args[b.index]
         self._fill_hyper(a, self.opt.param_groups[b.group_index])
         a.lr_scale = self.lr_scale.data_ptr() if self.lr_scale is not None else 0
@@ -251,14 +301,14 @@ class FusedEngine:
                     self.symm.allreduce_(s1)
             for s in b.slots:
                 st = opt.state[s.param]
-                v0 = s0[s.offset: s.offset + s.numel].view(s.param.shape)
+                v0 = arena_view(s0, s.offset, s.param)
                 if self.kind == "sgd":
                     if opt.param_groups[b.group_index].get("momentum", 0.0) != 0.0:
                         st["momentum_buffer"] = v0
                 else:
                     st["step"] = torch.tensor(float(steps_dev))
                     st["exp_avg"] = v0
-                    st["exp_avg_sq"] = s1[s.offset: s.offset + s.numel].view(s.param.shape)
+                    st["exp_avg_sq"] = arena_view(s1, s.offset, s.param)
         self._state_dirty = False
 
     def import_state(self):
@@ -273,12 +323,12 @@ class FusedEngine:
                 if self.kind == "sgd":
                     mb = st.get("momentum_buffer")
                     if mb is not None:
-                        ar["S0"][lo: lo + s.numel].copy_(mb.reshape(-1).float())
+                        arena_view(ar["S0"], lo, s.param).copy_(mb)
                         steps = max(steps, 1)
                 else:
                     if "exp_avg" in st:
-                        ar["S0"][lo: lo + s.numel].copy_(st["exp_avg"].reshape(-1).float())
-                        ar["S1"][lo: lo + s.numel].copy_(st["exp_avg_sq"].reshape(-1).float())
+                        arena_view(ar["S0"], lo, s.param).copy_(st["exp_avg"])
+                        arena_view(ar["S1"], lo, s.param).copy_(st["exp_avg_sq"])
                         steps = max(steps, int(float(st.get("step", 0))))
             if self._sharded(b):
                 # keep only the owned slice (others must stay zero for export's Sum-gather)

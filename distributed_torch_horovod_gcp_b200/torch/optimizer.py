@@ -163,16 +163,27 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         return flat[b.flat_offset: b.flat_offset + b.numel]
 
     def _register_hooks(self):
+        from ..ops.grad_sink import ParamSink
         for b in self._buckets:
             for s in b.slots:
-                h = s.param.register_post_accumulate_grad_hook(self._make_hook(s.param))
+                hook = self._make_hook(s.param)
+                h = s.param.register_post_accumulate_grad_hook(hook)
                 self._hook_handles.append(h)
+                if self._engine is not None:
+                    # weight-gradient kernels may write straight into the bucket slot and then run the
+                    # same bucket-ready logic autograd's AccumulateGrad would (ops/grad_sink.py)
+                    s.param._b200dp_sink = ParamSink(
+                        (lambda pid=id(s.param): self._passes[pid]),
+                        (lambda p=s.param, hk=hook: hk(p)))
 
     # ------------------------------------------------------------------ hooks
     def _make_hook(self, p):
         pid = id(p)
 
         def hook(param):
+            sink = getattr(param, "_b200dp_sink", None)
+            if sink is not None:
+                sink.reset()
             b = self._bucket_of[pid]
             if b.index in self._launched:
                 raise AssertionError(
@@ -284,6 +295,11 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         self._launched.clear()
         for b in self._buckets:
             self._pending[b.index] = len(b.slots)
+            if self._engine is not None:
+                for s in b.slots:
+                    sink = getattr(s.param, "_b200dp_sink", None)
+                    if sink is not None:
+                        sink.reset()
         for k in self._passes:
             self._passes[k] = 0
         self._synchronized = True
@@ -402,6 +418,10 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         for h in self._hook_handles:
             h.remove()
         self._hook_handles.clear()
+        for b in self._buckets:
+            for s in b.slots:
+                if hasattr(s.param, "_b200dp_sink"):
+                    del s.param._b200dp_sink
 
 
 def DistributedOptimizer(optimizer, named_parameters=None, compression=Compression.none,
