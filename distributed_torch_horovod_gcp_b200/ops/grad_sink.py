@@ -27,17 +27,29 @@ _ENABLED = os.environ.get("B200DP_GRAD_SINK", "1") == "1"
 
 
 class ParamSink:
-    __slots__ = ("uses", "multi", "passes_done", "fire")
+    __slots__ = ("uses", "multi", "manual", "passes_done", "_fire")
 
     def __init__(self, passes_done: Callable[[], int], fire: Callable[[], None]):
         self.uses = 0
         self.multi = False
+        self.manual = False                 # the kernel path already ran the bucket-ready logic
         self.passes_done = passes_done      # backward passes already accumulated in the slot
-        self.fire = fire                    # the optimizer's post-accumulate hook for this param
+        self._fire = fire                   # the optimizer's post-accumulate hook for this param
+
+    def fire(self):
+        """Run the bucket-ready logic now.  Autograd still evaluates the parameter's AccumulateGrad
+        node with an undefined gradient (no kernels) and — depending on the PyTorch version — calls
+        the post-accumulate hook again; ``manual`` makes that second call a no-op."""
+        self._fire()
+        self.manual = True
 
     def reset(self):
         self.uses = 0
         self.multi = False
+
+    def reset_step(self):
+        self.reset()
+        self.manual = False
 
 
 def note_forward(weight) -> None:

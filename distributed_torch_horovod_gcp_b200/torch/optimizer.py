@@ -183,6 +183,9 @@ class _DistributedOptimizer(torch.optim.Optimizer):
         def hook(param):
             sink = getattr(param, "_b200dp_sink", None)
             if sink is not None:
+                if sink.manual:            # the weight-gradient kernel already reported this pass
+                    sink.manual = False
+                    return
                 sink.reset()
             b = self._bucket_of[pid]
             if b.index in self._launched:
@@ -299,7 +302,7 @@ class _DistributedOptimizer(torch.optim.Optimizer):
                 for s in b.slots:
                     sink = getattr(s.param, "_b200dp_sink", None)
                     if sink is not None:
-                        sink.reset()
+                        sink.reset_step()
         for k in self._passes:
             self._passes[k] = 0
         self._synchronized = True
