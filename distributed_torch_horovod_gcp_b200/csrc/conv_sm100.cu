@@ -28,6 +28,7 @@
 #include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "sm100_common.cuh"
@@ -41,10 +42,13 @@ struct ConvTap {
   int amap;      // which activation view (parity) the tap reads
   int dw, dh;    // box shift in that view
   int wcol;      // fprop/dgrad: column of the [Cout][R*S*Cin] weight matrix; wgrad: output column
+  int row_off;   // halo kernel: first row of this tap's 8 x 16 sub-view inside the halo box
 };
 struct ConvClass {
   int ntaps;
   int out_map;   // which output view (dgrad stride 2: parity of dx)
+  // halo kernel: ONE box {64 c, gw, gh, 1} at shift (dw0, dh0) serves every tap of the class
+  int amap, dw0, dh0, gw, gh;
   ConvTap taps[MAX_TAPS];
 };
 struct ConvParams {
@@ -279,6 +283,209 @@ conv_bf16_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   }
 }
 
+
+// ====================================================================================================
+// Halo variant (3x3 stride-1 fprop/dgrad, stride-2 dgrad).  The kernel above fetches the activation
+// box once PER TAP, i.e. 9x from L2 — measured: it runs at the L2->SM bandwidth roofline
+// (256*BN/(256+2*BN) FLOP/B: 350/650/870 TFLOP/s for BN = 64/128/256; benchmarks/conv_bench.py).
+// Here an M tile is 8 (w) x 16 (h) output pixels of one image and, per 64-channel chunk, ONE TMA box
+// {64 c, 8+2, 16+2, 1} brings the tile with its halo (1.4x the tile instead of 9x).  Each 8-row UMMA
+// core group is one w-line of the box, so tap (r, s) is the SAME shared-memory image read through a
+// descriptor whose start address is advanced by (r*gw + s) rows and whose 8-row-group stride (SBO)
+// is the box line pitch gw*128 B.  The 128B swizzle is a function of the absolute smem address for
+// both the TMA write and the UMMA read, which is what makes row-shifted views legal.
+// Two rings: A (halo boxes, 24 KB) and B (weight tiles), because one A box feeds nine B tiles.
+// ====================================================================================================
+constexpr int HALO_BW = 8, HALO_BH = 16;
+constexpr int HALO_A_BYTES = 24 * 1024;          // (8+2)*(16+2)*128 B = 23040, rounded to 1024
+constexpr int HALO_A_STAGES = 3;
+template <int BN>
+struct HaloCfg {
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_STAGES = (BN == 256) ? 3 : ((BN == 128) ? 6 : 8);
+  static constexpr int STORE_BYTES = EPI_WARPS * 4096;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = HALO_A_STAGES * HALO_A_BYTES + B_STAGES * B_BYTES + STORE_BYTES + 1024 + 256;
+};
+
+template <int BN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvParams p) {
+  using C = HaloCfg<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + HALO_A_STAGES * HALO_A_BYTES;
+  uint8_t* smem_store = smem_b + C::B_STAGES * C::B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_store + C::STORE_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + HALO_A_STAGES;
+  uint64_t* b_full = a_empty + HALO_A_STAGES;
+  uint64_t* b_empty = b_full + C::B_STAGES;
+  uint64_t* tmem_full = b_empty + C::B_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.out[i]);
+    for (int i = 0; i < HALO_A_STAGES; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < C::B_STAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_base_slot)),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int nnb = p.g.num_n_blocks;
+  const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int work_items = p.num_classes * pix_tiles * nnb;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+        const int nt = w % nnb;
+        const int rest = w / nnb;
+        const int mt = rest % pix_tiles;
+        const ConvClass& cl = p.cls[rest / pix_tiles];
+        const int w0 = (mt % p.tiles_w) * HALO_BW;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * HALO_BH;
+        const int n0 = mt / (p.tiles_w * p.tiles_h);
+        const int n_idx = nt * BN;
+        const uint32_t a_bytes = (uint32_t)cl.gw * (uint32_t)cl.gh * 128u;
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_expect_tx(&a_full[sa], a_bytes);
+          tma_load_4d(&maps.a[cl.amap], &a_full[sa], smem_a + sa * HALO_A_BYTES, kc * BLOCK_K, w0 + cl.dw0,
+                      h0 + cl.dh0, n0);
+          if (++sa == HALO_A_STAGES) { sa = 0; pa ^= 1; }
+          for (int t = 0; t < cl.ntaps; ++t) {
+            const int wcol = cl.taps[t].wcol;
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_expect_tx(&b_full[sb], C::B_BYTES);
+            uint8_t* dst = smem_b + sb * C::B_BYTES;
+            if (!B_MN) {
+              tma_load_2d(&maps.b, &b_full[sb], dst, wcol + kc * BLOCK_K, n_idx);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_2d(&maps.b, &b_full[sb], dst + c * (BLOCK_K * 128), wcol + n_idx + 64 * c, kc * BLOCK_K);
+            }
+            if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    constexpr uint32_t idesc = make_idesc<BN, false, B_MN>();
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+      const ConvClass& cl = p.cls[(w / nnb) / pix_tiles];
+      const uint32_t sbo = (uint32_t)cl.gw * 128u;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+        mbar_wait(&a_full[sa], pa);
+        const uint32_t a_base = smem_u32(smem_a + sa * HALO_A_BYTES);
+        for (int t = 0; t < cl.ntaps; ++t) {
+          mbar_wait(&b_full[sb], pb);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_tap = a_base + (uint32_t)cl.taps[t].row_off * 128u;
+            const uint32_t b_base = smem_u32(smem_b + sb * C::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t da = make_desc(a_tap + k * (UMMA_K * 2), 16, sbo);
+              const uint64_t db = B_MN ? make_desc(b_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                       : make_desc(b_base + k * (UMMA_K * 2), 16, 1024);
+              tc_mma_bf16(d_tmem, da, db, idesc, (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit(&b_empty[sb]);
+            if (t == cl.ntaps - 1) {
+              tc_commit(&a_empty[sa]);
+              if (kc == p.kc_per_tap - 1) tc_commit(&tmem_full[acc]);
+            }
+          }
+          __syncwarp();
+          if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
+        }
+        if (++sa == HALO_A_STAGES) { sa = 0; pa ^= 1; }
+      }
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ============================ epilogue warps ============================
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int half = (warp - 2) >> 2;
+    const int c_begin = (BN >= 128) ? half * (BN / 2) : 0;
+    const int c_end = (BN >= 128) ? c_begin + BN / 2 : (half == 0 ? BN : 0);
+    uint8_t* my_store = smem_store + (warp - 2) * 4096;
+    for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int nt = w % nnb;
+      const int rest = w / nnb;
+      const int mt = rest % pix_tiles;
+      const ConvClass& cl = p.cls[rest / pix_tiles];
+      StoreAt at;
+      at.rank4 = 1;                                              // slab q = lines 4q..4q+3 of the 8 x 16 tile
+      at.w = (mt % p.tiles_w) * HALO_BW;
+      at.h = ((mt / p.tiles_w) % p.tiles_h) * HALO_BH + 4 * q;
+      at.n = mt / (p.tiles_w * p.tiles_h);
+      at.c_ptr = nullptr;
+      epilogue_rows<BN>(p.g, &maps.out[cl.out_map], nullptr, tmem_base, acc, q, lane, 0, nt * BN, c_begin, c_end,
+                        my_store, at);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)C::TMEM_COLS)
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -410,6 +617,68 @@ int launch_conv(const ConvMaps& maps, const ConvParams& p, int BN, int work, int
   return fail("block_n must be 64/128/256");
 }
 
+
+bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200DP_CONV_HALO");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// Re-plan a fprop/dgrad launch for the halo kernel: 8 x 16 x 1 pixel tiles, one activation box per class.
+// `a_ptr` is the dense NHWC tensor {C, Wd, Hd, Nd} the taps read (x for fprop, dy for dgrad).
+int setup_halo(ConvMaps& maps, ConvParams& p, const void* a_ptr, int C, int Wd, int Hd, int Nd) {
+  p.bw = HALO_BW; p.bh = HALO_BH; p.bn = 1;
+  p.tiles_w = (Wd + HALO_BW - 1) / HALO_BW;
+  p.tiles_h = (Hd + HALO_BH - 1) / HALO_BH;
+  p.tiles_n = Nd;
+  for (int ci = 0; ci < p.num_classes; ++ci) {
+    ConvClass& cl = p.cls[ci];
+    int lo_w = 1 << 30, hi_w = -(1 << 30), lo_h = 1 << 30, hi_h = -(1 << 30);
+    for (int t = 0; t < cl.ntaps; ++t) {
+      lo_w = cl.taps[t].dw < lo_w ? cl.taps[t].dw : lo_w; hi_w = cl.taps[t].dw > hi_w ? cl.taps[t].dw : hi_w;
+      lo_h = cl.taps[t].dh < lo_h ? cl.taps[t].dh : lo_h; hi_h = cl.taps[t].dh > hi_h ? cl.taps[t].dh : hi_h;
+    }
+    cl.amap = ci; cl.dw0 = lo_w; cl.dh0 = lo_h;
+    cl.gw = HALO_BW + (hi_w - lo_w); cl.gh = HALO_BH + (hi_h - lo_h);
+    if (cl.gw * cl.gh * 128 > HALO_A_BYTES) return fail("halo box too large");
+    for (int t = 0; t < cl.ntaps; ++t)
+      cl.taps[t].row_off = (cl.taps[t].dh - lo_h) * cl.gw + (cl.taps[t].dw - lo_w);
+    if (make_map4(&maps.a[ci], a_ptr, C, Wd, Hd, Nd, C, (uint64_t)Wd * C, (uint64_t)Hd * Wd * C, cl.gw, cl.gh, 1))
+      return -1;
+  }
+  for (int ci = p.num_classes; ci < 4; ++ci) maps.a[ci] = maps.a[0];
+  return 0;
+}
+
+template <bool B_MN>
+int launch_halo(const ConvMaps& maps, const ConvParams& p, int BN, int work, int max_ctas, cudaStream_t st) {
+  int grid = work < g_num_sms ? work : g_num_sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+#define HALO_LAUNCH(BNV)                                                                                \
+  if (BN == BNV) {                                                                                      \
+    auto kern = conv_halo_kernel<BNV, B_MN>;                                                            \
+    static bool attr_set = false;                                                                       \
+    if (!attr_set) {                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                           HaloCfg<BNV>::SMEM_BYTES);                                   \
+      if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);                                 \
+      attr_set = true;                                                                                  \
+    }                                                                                                   \
+    kern<<<grid, NUM_THREADS, HaloCfg<BNV>::SMEM_BYTES, st>>>(maps, p);                                 \
+    cudaError_t e = cudaGetLastError();                                                                 \
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);                                   \
+    return 0;                                                                                           \
+  }
+  HALO_LAUNCH(64)
+  HALO_LAUNCH(128)
+  HALO_LAUNCH(256)
+#undef HALO_LAUNCH
+  return fail("block_n must be 64/128/256");
+}
+
 void init_gemm_params(GemmParams& g) {
   memset(&g, 0, sizeof(g));
   g.M = INT_MAX;
@@ -463,7 +732,10 @@ int b200dp_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W
       }
       t.wcol = (r * S + c) * Cin;
     }
-  if (stride == 1) {
+  const bool halo = halo_enabled() && R == 3 && stride == 1 && s.OH >= 12 && s.OW >= 8;
+  if (halo) {
+    if (setup_halo(maps, p, x, Cin, W, H, N)) return -1;
+  } else if (stride == 1) {
     if (make_map4(&maps.a[0], x, Cin, W, H, N, Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin, p.bw, p.bh, p.bn))
       return -1;
     maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
@@ -478,6 +750,7 @@ int b200dp_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W
     return -1;
   maps.out[1] = maps.out[2] = maps.out[3] = maps.out[0];
   const int work = p.tiles_w * p.tiles_h * p.tiles_n * p.g.num_n_blocks;
+  if (halo) return launch_halo<false>(maps, p, BN, work, max_ctas, (cudaStream_t)(uintptr_t)stream);
   return launch_conv<MODE_FPROP>(maps, p, BN, work, max_ctas, (cudaStream_t)(uintptr_t)stream);
 }
 
@@ -501,12 +774,16 @@ int b200dp_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int
   choose_box(s.OW, s.OH, N, BLOCK_M, &p.bw, &p.bh, &p.bn);   // stride 2: each dx parity view is OW x OH
   p.tiles_w = (s.OW + p.bw - 1) / p.bw; p.tiles_h = (s.OH + p.bh - 1) / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
   p.num_taps_total = R * S;
+  const bool halo = halo_enabled() && R == 3 && s.OH >= 12 && s.OW >= 8;
+  if (halo) { p.bw = HALO_BW; p.bh = HALO_BH; p.bn = 1; }
   int sw, sh, sn;
   slab_box(p.bw, p.bh, p.bn, &sw, &sh, &sn);
-  if (make_map4(&maps.a[0], dy, Cout, s.OW, s.OH, N, Cout, (uint64_t)s.OW * Cout, (uint64_t)s.OH * s.OW * Cout,
-                p.bw, p.bh, p.bn))
-    return -1;
-  maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  if (!halo) {
+    if (make_map4(&maps.a[0], dy, Cout, s.OW, s.OH, N, Cout, (uint64_t)s.OW * Cout, (uint64_t)s.OH * s.OW * Cout,
+                  p.bw, p.bh, p.bn))
+      return -1;
+    maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  }
   if (make_map2(&maps.b, w, Cout, (uint64_t)R * S * Cin, (uint64_t)R * S * Cin, 64)) return -1;
   if (stride == 1) {
     p.num_classes = 1;
@@ -544,7 +821,9 @@ int b200dp_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int
       if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);
     }
   }
+  if (halo && setup_halo(maps, p, dy, Cout, s.OW, s.OH, N)) return -1;
   const int work = p.num_classes * p.tiles_w * p.tiles_h * p.tiles_n * p.g.num_n_blocks;
+  if (halo) return launch_halo<true>(maps, p, BN, work, max_ctas, st);
   return launch_conv<MODE_DGRAD>(maps, p, BN, work, max_ctas, st);
 }
 

@@ -100,35 +100,61 @@ def test_resnet_block_uses_no_cudnn_conv():
 
 
 def test_grad_sink_matches_autograd_path():
-    """Training ResNet-18 (BasicBlocks: every conv is a 3x3) for 3 fused steps with weight gradients
-    written straight into the gradient buckets == the same run through autograd's AccumulateGrad."""
+    """Weight gradients written straight into the gradient buckets (ops/grad_sink.py) == the same
+    backward through autograd's AccumulateGrad.  The net has no batch-norm (its fp32-atomic batch
+    statistics make a deep random-init net chaotic at bf16 resolution), so the forward is
+    deterministic and the two gradient sets must agree to split-K rounding."""
     import os
     os.environ["B200DP_FUSED_SINGLE"] = "1"
+    import torch.nn as nn
     import distributed_torch_horovod_gcp_b200.torch as hvd
-    from distributed_torch_horovod_gcp_b200.models import resnet18
-    from distributed_torch_horovod_gcp_b200.ops import grad_sink
+    from distributed_torch_horovod_gcp_b200.ops import grad_sink, functional as F2, kernels
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c1 = nn.Conv2d(16, 64, 3, 1, 1, bias=False)
+            self.c2 = nn.Conv2d(64, 128, 3, 2, 1, bias=False)
+            self.c3 = nn.Conv2d(128, 256, 1, 2, 0, bias=False)
+            self.c4 = nn.Conv2d(256, 256, 1, 1, 0, bias=False)
+            self.fc = nn.Linear(256, 16)
+
+        def forward(self, x):
+            from distributed_torch_horovod_gcp_b200.ops.bn import conv2d
+            for c in (self.c1, self.c2, self.c3, self.c4):
+                x = torch.relu(conv2d(x, c))
+            return F2.linear(x.mean(dim=(2, 3)), self.fc.weight, self.fc.bias)
+
     hvd.init()
-    results = []
+    kernels.has("conv_implicit_gemm")
+    grads = []
     for enabled in (True, False):
         grad_sink._ENABLED = enabled
         torch.manual_seed(0)
-        model = resnet18(num_classes=10).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+        model = Net().cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
         opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9),
-                                       named_parameters=model.named_parameters())
+                                       named_parameters=model.named_parameters(),
+                                       backward_passes_per_step=2)
         assert opt.fused_engine is not None
-        x = torch.randn(8, 3, 64, 64, device="cuda").to(torch.bfloat16).contiguous(
+        x = torch.randn(8, 16, 32, 32, device="cuda").to(torch.bfloat16).contiguous(
             memory_format=torch.channels_last)
-        y = torch.randint(0, 10, (8,), device="cuda")
-        for _ in range(3):
-            loss = F.cross_entropy(model(x).float(), y)
-            loss.backward()
-            opt.step()
-            opt.zero_grad()
+        y = torch.randint(0, 16, (8,), device="cuda")
+        F.cross_entropy(model(x).float(), y).backward()      # pass 1 of 2: gradients stay in the buckets
         torch.cuda.synchronize()
-        results.append([p.detach().float().clone() for p in model.parameters()])
+        g1 = {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
+        F.cross_entropy(model(x).float(), y).backward()      # pass 2 accumulates on top (accumulate path)
+        torch.cuda.synchronize()
+        g2 = {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
+        opt.step()
+        opt.zero_grad()
+        torch.cuda.synchronize()
+        grads.append((g1, g2))
         opt.remove_hooks()
     grad_sink._ENABLED = True
     hvd.shutdown()
-    for a, b in zip(*results):
-        assert torch.isfinite(a).all()
-        torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-3)
+    (a1, a2), (b1, b2) = grads
+    for n in a1:
+        assert a1[n].abs().sum() > 0, n
+        assert _rel(a1[n], b1[n]) < 1e-2, (n, _rel(a1[n], b1[n]))
+        assert _rel(a2[n], b2[n]) < 1e-2, (n, _rel(a2[n], b2[n]))
+        assert _rel(a2[n], 2 * a1[n]) < 2e-2, n
