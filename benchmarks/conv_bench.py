@@ -54,6 +54,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--out", default="gpurun_out/conv_bench.json")
+    ap.add_argument("--only", type=int, default=-1, help="run a single shape index")
+    ap.add_argument("--ours-only", action="store_true", help="skip the cuDNN arm (for ncu captures)")
     args = ap.parse_args()
     from distributed_torch_horovod_gcp_b200.ops import kernels, conv as C
     assert kernels.has("conv_implicit_gemm")
@@ -67,7 +69,8 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     rows = []
     N = args.batch
-    for (ci, H, W, co, R, s) in SHAPES:
+    shapes = SHAPES if args.only < 0 else [SHAPES[args.only]]
+    for (ci, H, W, co, R, s) in shapes:
         pad = (R - 1) // 2
         x = torch.randn(N, ci, H, W, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         w = (torch.randn(co, ci, R, R, device="cuda") * 0.05).to(torch.bfloat16).contiguous(
@@ -80,6 +83,9 @@ def main():
             "dgrad": timeit(lambda: C.conv_dgrad(dy, w, x.shape, s, pad), args.iters, flush),
             "wgrad": timeit(lambda: C.conv_wgrad(dy, x, w, s, pad), args.iters, flush),
         }
+        if args.ours_only:
+            print(json.dumps({"shape": f"N{N} {ci}x{H}x{W} -> {co} k{R} s{s}", "ours_us": ours}), flush=True)
+            continue
         xg = x.detach().clone().requires_grad_(True)
         wg = w.detach().clone().requires_grad_(True)
         yc = F.conv2d(xg, wg, None, s, pad)
@@ -97,6 +103,8 @@ def main():
         rows.append(row)
         print(json.dumps(row), flush=True)
         del x, w, y, dy, xg, wg, yc
+    if args.ours_only:
+        return
     tot_o = sum(r[k]["ours_us"] for r in rows for k in ("fprop", "dgrad", "wgrad"))
     tot_c = sum(r[k]["cudnn_us"] for r in rows for k in ("fprop", "dgrad", "wgrad"))
     summary = {"total_ours_us": round(tot_o, 1), "total_cudnn_us": round(tot_c, 1), "peak_tflops": peak}

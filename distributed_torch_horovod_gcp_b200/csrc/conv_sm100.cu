@@ -190,45 +190,47 @@ conv_bf16_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer ============================
-    constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
-      int nkb;
-      if (MODE != MODE_WGRAD) {
-        nkb = p.cls[(w / nnb) / pix_tiles].ntaps * p.kc_per_tap;
-      } else {
-        const int kb0 = (w / tiles) * kb_per_split;
-        nkb = min(kb0 + kb_per_split, pix_tiles) - kb0;
-      }
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ============================ MMA issuer (one elected thread) ============================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+      constexpr uint32_t KSTEP_A = A_MN ? ((UMMA_K * 128) >> 4) : ((UMMA_K * 2) >> 4);
+      constexpr uint32_t KSTEP_B = B_MN ? ((UMMA_K * 128) >> 4) : ((UMMA_K * 2) >> 4);
+      const uint64_t a0 = (A_MN ? make_desc_base(BLOCK_K * 128, 1024) : make_desc_base(16, 1024)) +
+                          desc_addr(smem_u32(smem_a));
+      const uint64_t b0 = (B_MN ? make_desc_base(BLOCK_K * 128, 1024) : make_desc_base(16, 1024)) +
+                          desc_addr(smem_u32(smem_b));
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+        int nkb;
+        if (MODE != MODE_WGRAD) {
+          nkb = p.cls[(w / nnb) / pix_tiles].ntaps * p.kc_per_tap;
+        } else {
+          const int kb0 = (w / tiles) * kb_per_split;
+          nkb = min(kb0 + kb_per_split, pix_tiles) - kb0;
+        }
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accum = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = a0 + (uint64_t)(stage * (C::A_BYTES >> 4));
+          const uint64_t db = b0 + (uint64_t)(stage * (C::B_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                     : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                     : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            tc_mma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16(d_tmem, da + k * KSTEP_A, db + k * KSTEP_B, idesc, accum);
+            accum = 1;
           }
           tc_commit(&empty_bar[stage]);
-          if (kb == nkb - 1) tc_commit(&tmem_full[acc]);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        tc_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ============================ epilogue warps ============================
@@ -403,47 +405,54 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer ============================
-    constexpr uint32_t idesc = make_idesc<BN, false, B_MN>();
-    int sa = 0, sb = 0;
-    uint32_t pa = 0, pb = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
-      const ConvClass& cl = p.cls[(w / nnb) / pix_tiles];
-      const uint32_t sbo = (uint32_t)cl.gw * 128u;
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int kc = 0; kc < p.kc_per_tap; ++kc) {
-        mbar_wait(&a_full[sa], pa);
-        const uint32_t a_base = smem_u32(smem_a + sa * HALO_A_BYTES);
-        for (int t = 0; t < cl.ntaps; ++t) {
-          mbar_wait(&b_full[sb], pb);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_tap = a_base + (uint32_t)cl.taps[t].row_off * 128u;
-            const uint32_t b_base = smem_u32(smem_b + sb * C::B_BYTES);
+    // ============================ MMA issuer (one elected thread) ============================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc<BN, false, B_MN>();
+      constexpr uint32_t KSTEP_A = (UMMA_K * 2) >> 4;                            // 32 B along K (K-major)
+      constexpr uint32_t KSTEP_B = B_MN ? ((UMMA_K * 128) >> 4) : ((UMMA_K * 2) >> 4);
+      const uint64_t b_hi = B_MN ? make_desc_base(BLOCK_K * 128, 1024) : make_desc_base(16, 1024);
+      const uint64_t b0 = b_hi + desc_addr(smem_u32(smem_b));
+      const uint32_t a0 = smem_u32(smem_a);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+        const ConvClass& cl = p.cls[(w / nnb) / pix_tiles];
+        const int ntaps = cl.ntaps;
+        const uint64_t a_hi = make_desc_base(16, (uint32_t)cl.gw * 128u);
+        uint32_t row_desc[MAX_TAPS];                                             // (row_off * 128) >> 4
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t da = make_desc(a_tap + k * (UMMA_K * 2), 16, sbo);
-              const uint64_t db = B_MN ? make_desc(b_base + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                       : make_desc(b_base + k * (UMMA_K * 2), 16, 1024);
-              tc_mma_bf16(d_tmem, da, db, idesc, (kc > 0 || t > 0 || k > 0) ? 1u : 0u);
-            }
-            tc_commit(&b_empty[sb]);
-            if (t == cl.ntaps - 1) {
-              tc_commit(&a_empty[sa]);
-              if (kc == p.kc_per_tap - 1) tc_commit(&tmem_full[acc]);
+        for (int t = 0; t < MAX_TAPS; ++t) row_desc[t] = (uint32_t)cl.taps[t].row_off << 3;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accum = 0;
+        for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          mbar_wait(&a_full[sa], pa);
+          const uint64_t a_st = a_hi + desc_addr(a0 + sa * HALO_A_BYTES);
+#pragma unroll
+          for (int t = 0; t < MAX_TAPS; ++t) {
+            if (t < ntaps) {
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              const uint64_t da = a_st + row_desc[t];
+              const uint64_t db = b0 + (uint64_t)(sb * (C::B_BYTES >> 4));
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                tc_mma_bf16(d_tmem, da + k * KSTEP_A, db + k * KSTEP_B, idesc, accum);
+                accum = 1;
+              }
+              tc_commit(&b_empty[sb]);
+              if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
             }
           }
-          __syncwarp();
-          if (++sb == C::B_STAGES) { sb = 0; pb ^= 1; }
+          tc_commit(&a_empty[sa]);
+          if (++sa == HALO_A_STAGES) { sa = 0; pa ^= 1; }
         }
-        if (++sa == HALO_A_STAGES) { sa = 0; pa ^= 1; }
+        tc_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ============================ epilogue warps ============================

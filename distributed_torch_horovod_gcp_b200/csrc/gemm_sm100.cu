@@ -118,41 +118,43 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer ============================
-    constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
-      const int split = w / tiles;
-      const int kb0 = split * kb_per_split;
-      const int kb1 = min(kb0 + kb_per_split, p.num_k_blocks);
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ============================ MMA issuer (one elected thread) ============================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc<BN, A_MN, B_MN>();
+      constexpr uint32_t KSTEP_A = A_MN ? ((UMMA_K * 128) >> 4) : ((UMMA_K * 2) >> 4);
+      constexpr uint32_t KSTEP_B = B_MN ? ((UMMA_K * 128) >> 4) : ((UMMA_K * 2) >> 4);
+      const uint64_t a0 = (A_MN ? make_desc_base(BLOCK_K * 128, 1024) : make_desc_base(16, 1024)) +
+                          desc_addr(smem_u32(smem_a));
+      const uint64_t b0 = (B_MN ? make_desc_base(BLOCK_K * 128, 1024) : make_desc_base(16, 1024)) +
+                          desc_addr(smem_u32(smem_b));
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+        const int split = w / tiles;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, p.num_k_blocks);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
-          const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t accum = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = a0 + (uint64_t)(stage * (C::A_BYTES >> 4));
+          const uint64_t db = b0 + (uint64_t)(stage * (C::B_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                     : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                     : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-            tc_mma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            tc_mma_bf16(d_tmem, da + k * KSTEP_A, db + k * KSTEP_B, idesc, accum);
+            accum = 1;
           }
-          tc_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
-          if (kb == kb1 - 1) tc_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+          tc_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        tc_commit(&tmem_full[acc]);                       // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ============================ epilogue warps ============================
@@ -347,8 +349,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer (leader CTA only) ============================
-    if (leader) {
+    // ============================ MMA issuer (leader CTA only, one elected thread) ============================
+    if (leader && elect_one()) {
       uint32_t idesc = 0;
       idesc |= 1u << 4;
       idesc |= 1u << 7;
@@ -357,6 +359,12 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       idesc |= (B_MN ? 1u : 0u) << 16;
       idesc |= (uint32_t)(BN2 >> 3) << 17;
       idesc |= (uint32_t)((2 * BLOCK_M) >> 4) << 24;       // UMMA M = 256 across the CTA pair
+      constexpr uint32_t KSTEP_A = A_MN ? ((UMMA_K * 128) >> 4) : ((UMMA_K * 2) >> 4);
+      constexpr uint32_t KSTEP_B = B_MN ? ((UMMA_K * 128) >> 4) : ((UMMA_K * 2) >> 4);
+      const uint64_t a0 = (A_MN ? make_desc_base(BLOCK_K * 128, 1024) : make_desc_base(16, 1024)) +
+                          desc_addr(smem_u32(smem_a));
+      const uint64_t b0 = (B_MN ? make_desc_base(BLOCK_K * 128, 1024) : make_desc_base(16, 1024)) +
+                          desc_addr(smem_u32(smem_b));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -368,26 +376,21 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2);
+        uint32_t accum = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sa = smem_u32(smem_a + stage * C::A_BYTES);
-            const uint32_t sb = smem_u32(smem_b + stage * C::B_BYTES);
+          const uint64_t da = a0 + (uint64_t)(stage * (C::A_BYTES >> 4));
+          const uint64_t db = b0 + (uint64_t)(stage * (C::B_BYTES >> 4));
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                       : make_desc(sa + k * (UMMA_K * 2), 16, 1024);
-              const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                       : make_desc(sb + k * (UMMA_K * 2), 16, 1024);
-              tc_mma_bf16_2cta(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
-            tc_commit_2cta(&empty_bar[stage]);                  // frees the stage in BOTH CTAs
-            if (kb == kb1 - 1) tc_commit_2cta(&tmem_full[acc]);  // accumulators ready in BOTH CTAs
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            tc_mma_bf16_2cta(d_tmem, da + k * KSTEP_A, db + k * KSTEP_B, idesc, accum);
+            accum = 1;
           }
-          __syncwarp();
+          tc_commit_2cta(&empty_bar[stage]);                  // frees the stage in BOTH CTAs
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        tc_commit_2cta(&tmem_full[acc]);                      // accumulators ready in BOTH CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -165,6 +165,29 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
+// One elected lane of a converged warp (PTX elect.sync).  Code guarded by it is known to the compiler
+// to run in a single thread, so tcgen05 / TMA operands stay in uniform registers instead of going
+// through a per-instruction ELECT + R2UR + BRA.U.ANY sequence (what `lane == 0` compiles to).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Descriptor without the start address (bits 0..13): OR / add `(smem_addr >> 4)` to place it; advancing
+// along K or by whole rows is then a 64-bit add of `(bytes >> 4)` — no rebuild in the MMA issue loop,
+// which is a single thread and the critical path of every tcgen05 kernel here (profiles/ncu_conv_*.md).
+__device__ __forceinline__ uint64_t make_desc_base(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_desc(0, lbo_bytes, sbo_bytes);
+}
+__device__ __forceinline__ uint64_t desc_addr(uint32_t smem_addr) { return (uint64_t)((smem_addr & 0x3FFFF) >> 4); }
+
 template <int BN, bool A_MN, bool B_MN>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
   uint32_t d = 0;

@@ -134,17 +134,18 @@ def test_grad_sink_matches_autograd_path():
         model = Net().cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
         opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9),
                                        named_parameters=model.named_parameters(),
-                                       backward_passes_per_step=2)
+                                       backward_passes_per_step=3)
         assert opt.fused_engine is not None
         x = torch.randn(8, 16, 32, 32, device="cuda").to(torch.bfloat16).contiguous(
             memory_format=torch.channels_last)
         y = torch.randint(0, 16, (8,), device="cuda")
-        F.cross_entropy(model(x).float(), y).backward()      # pass 1 of 2: gradients stay in the buckets
+        F.cross_entropy(model(x).float(), y).backward()      # pass 1 of 3: gradients stay in the buckets
         torch.cuda.synchronize()
         g1 = {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
         F.cross_entropy(model(x).float(), y).backward()      # pass 2 accumulates on top (accumulate path)
         torch.cuda.synchronize()
         g2 = {n: p.grad.detach().float().clone() for n, p in model.named_parameters()}
+        F.cross_entropy(model(x).float(), y).backward()      # pass 3 launches the buckets
         opt.step()
         opt.zero_grad()
         torch.cuda.synchronize()
