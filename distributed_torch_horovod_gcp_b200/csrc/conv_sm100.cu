@@ -495,6 +495,192 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   }
 }
 
+
+// ====================================================================================================
+// Weight gradient, halo variant (3x3, stride 1).  Work item = (pixel range, 64 input channels, 64 output
+// channels); it owns dW[co 0..63][all 9 taps][ci 0..63] for that pixel range, all nine taps resident in
+// TMEM (5 accumulators of 128 x 64: rows = {tap 2q | tap 2q+1} x 64 ci, columns = 64 co).
+// Per K block of 128 pixels (8 w x 16 lines) the CTA fetches ONE x box with halo {64 ci, 10, 18} and
+// ONE dy box {64 co, 8, 16}; the A operand of tap pair q is the x box seen through an MN-major
+// descriptor whose start is tap 2q's row shift and whose M-chunk stride (LBO) is the row distance to
+// tap 2q+1 — two taps are stacked along M without any data movement; the 8-pixel K groups are the
+// box's w-lines (SBO = line pitch).  39 KB of operands feed 5 x 8 UMMAs (128x64x16), i.e. the kernel is
+// tensor/smem bound instead of re-reading x nine times from L2 (plain wgrad: 24-48 KB per 128x64x64).
+// Small maps: lines of consecutive images are adjacent box lines (pitch gw), and the TMA zero-fills the
+// dy lines that fall outside an image, so a 7x7 map packs two images into the 16 lines of a K block.
+// Results leave through coalesced fp32 RED.ADDs into the [Cout][9*Cin] workspace (rows of an
+// accumulator are consecutive ci).
+// ====================================================================================================
+struct WgradHaloParams {
+  float* ws;
+  int Cin, Cout, ldc;
+  int ci_chunks, co_chunks, splits;
+  int tiles_w, tiles_h, tiles_n;     // K blocks: w tiles x line tiles x image groups
+  int nimg;                          // images per K block (2 for maps with H + 2 <= 9)
+  int line_step;                     // lines advanced per h tile (16) — one image per box when nimg == 1
+  int xbytes, ybytes;                // bytes of the two boxes (expect_tx)
+  int gw;                            // x box line pitch in pixels (10)
+  int row_off[MAX_TAPS];             // tap row shift inside the x box
+};
+constexpr int WH_X_BYTES = 24 * 1024;
+constexpr int WH_Y_BYTES = 18 * 1024;
+constexpr int WH_STAGE_BYTES = WH_X_BYTES + WH_Y_BYTES;
+constexpr int WH_STAGES = 5;
+constexpr int WH_SMEM_BYTES = WH_STAGES * WH_STAGE_BYTES + 1024 + 256;
+constexpr int WH_PAIRS = 5;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_y,
+                       const __grid_constant__ WgradHaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WH_STAGES * WH_STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + WH_STAGES;
+  uint64_t* tmem_full = bars + 2 * WH_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_y);
+    for (int i = 0; i < WH_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_base_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  const int chunk_pairs = p.ci_chunks * p.co_chunks;
+  const int work_items = chunk_pairs * p.splits;
+  const int kblocks = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int kb_per_split = (kblocks + p.splits - 1) / p.splits;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+        const int cp = w % chunk_pairs, split = w / chunk_pairs;
+        const int ci0 = (cp % p.ci_chunks) * 64, co0 = (cp / p.ci_chunks) * 64;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, kblocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int w0 = (kb % p.tiles_w) * 8;
+          const int h0 = ((kb / p.tiles_w) % p.tiles_h) * p.line_step;
+          const int n0 = (kb / (p.tiles_w * p.tiles_h)) * p.nimg;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], (uint32_t)(p.xbytes + p.ybytes));
+          uint8_t* sx = smem + stage * WH_STAGE_BYTES;
+          tma_load_4d(&map_x, &full_bar[stage], sx, ci0, w0 - 1, h0 - 1, n0);
+          tma_load_4d(&map_y, &full_bar[stage], sx + WH_X_BYTES, co0, w0, h0, n0);
+          if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // A: x box, MN-major (M = ci contiguous, K = pixels), 8-pixel K groups = box w-lines
+      // B: dy box, MN-major (N = co contiguous), dense 8 x 16 pixel box
+      constexpr uint32_t idesc = make_idesc<64, true, true>();
+      const uint32_t line_bytes = (uint32_t)p.gw * 128u;
+      uint64_t a_pair[WH_PAIRS];
+#pragma unroll
+      for (int q = 0; q < WH_PAIRS; ++q) {
+        const int t0 = 2 * q, t1 = (2 * q + 1 < MAX_TAPS) ? 2 * q + 1 : 2 * q;
+        const uint32_t lbo = (uint32_t)(p.row_off[t1] - p.row_off[t0]) * 128u;
+        a_pair[q] = make_desc_base(lbo, line_bytes) + (uint64_t)((uint32_t)p.row_off[t0] << 3);
+      }
+      const uint64_t b_base = make_desc_base(BLOCK_K * 128, 1024);
+      const uint32_t s0 = smem_u32(smem);
+      const uint32_t kstep_a = (2u * line_bytes) >> 4;       // 16 pixels = two w-lines of the x box
+      constexpr uint32_t kstep_b = (16 * 128) >> 4;          // 16 pixels = 16 rows of the dy box
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t item_phase = 0;
+      for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+        const int split = w / chunk_pairs;
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb0 + kb_per_split, kblocks);
+        mbar_wait(tmem_empty, item_phase ^ 1);
+        tc_fence_after();
+        uint32_t accum = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t ax = desc_addr(s0 + stage * WH_STAGE_BYTES);
+          const uint64_t by = b_base + desc_addr(s0 + stage * WH_STAGE_BYTES + WH_X_BYTES);
+#pragma unroll
+          for (int q = 0; q < WH_PAIRS; ++q) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              tc_mma_bf16(tmem_base + (uint32_t)(q * 64), a_pair[q] + ax + k * kstep_a, by + k * kstep_b, idesc,
+                          (k > 0) ? 1u : accum);
+          }
+          accum = 1;
+          tc_commit(&empty_bar[stage]);
+          if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tmem_full);
+        item_phase ^= 1;
+      }
+    }
+  } else {
+    // ============================ epilogue: coalesced fp32 RED.ADD ============================
+    const int q4 = warp & 3;                         // TMEM lane quarter: accumulator rows 32*q4 .. +31
+    const int half = (warp - 2) >> 2;                // pairs 0..2 | pairs 3..4
+    uint32_t item_phase = 0;
+    for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+      const int cp = w % chunk_pairs;
+      const int ci0 = (cp % p.ci_chunks) * 64, co0 = (cp / p.ci_chunks) * 64;
+      mbar_wait(tmem_full, item_phase);
+      tc_fence_after();
+      const int row = q4 * 32 + lane;                // 0..127: [tap 2q | tap 2q+1] x ci
+      const int ci = ci0 + (row & 63);
+      for (int q = half ? 3 : 0; q < (half ? 5 : 3); ++q) {
+        const int tap = 2 * q + (row >> 6);
+        uint32_t r[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(q * 64);
+        tc_ld_32x32b_x32(taddr, r);
+        tc_ld_32x32b_x32(taddr + 32, r + 32);
+        tc_wait_ld();
+        if (tap < MAX_TAPS && ci < p.Cin) {
+          float* dst = p.ws + (size_t)co0 * p.ldc + tap * p.Cin + ci;
+          const int nco = min(64, p.Cout - co0);
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i < nco) atomicAdd(dst + (size_t)i * p.ldc, __uint_as_float(r[i]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+      item_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -688,6 +874,62 @@ int launch_halo(const ConvMaps& maps, const ConvParams& p, int BN, int work, int
   return fail("block_n must be 64/128/256");
 }
 
+
+int launch_wgrad_halo(const void* dy, const void* x, void* dw_acc, const ConvShape& s, int splits, int max_ctas,
+                      cudaStream_t st) {
+  WgradHaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.ws = reinterpret_cast<float*>(dw_acc);
+  p.Cin = s.Cin; p.Cout = s.Cout; p.ldc = 9 * s.Cin;
+  p.ci_chunks = (s.Cin + 63) / 64; p.co_chunks = (s.Cout + 63) / 64;
+  p.gw = 10;
+  p.nimg = (s.H + 2 <= 9) ? 2 : 1;
+  const int xlines = (p.nimg == 2) ? (s.H + 2) : 18;      // lines of the x box per image
+  const int ylines = (p.nimg == 2) ? (s.H + 2) : 16;      // dy lines per image (rows past H are zero-filled)
+  p.line_step = 16;
+  p.tiles_w = (s.W + 7) / 8;
+  p.tiles_h = (p.nimg == 2) ? 1 : (s.H + 15) / 16;
+  p.tiles_n = (s.N + p.nimg - 1) / p.nimg;
+  p.xbytes = 10 * xlines * p.nimg * 128;
+  p.ybytes = 8 * ylines * p.nimg * 128;
+  if (p.xbytes > WH_X_BYTES || p.ybytes > WH_Y_BYTES) return fail("wgrad halo boxes too large");
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) p.row_off[r * 3 + c] = r * p.gw + c;
+  CUtensorMap mx, my;
+  if (make_map4(&mx, x, s.Cin, s.W, s.H, s.N, s.Cin, (uint64_t)s.W * s.Cin, (uint64_t)s.H * s.W * s.Cin, 10, xlines,
+                p.nimg))
+    return -1;
+  if (make_map4(&my, dy, s.Cout, s.W, s.H, s.N, s.Cout, (uint64_t)s.W * s.Cout, (uint64_t)s.H * s.W * s.Cout, 8,
+                ylines, p.nimg))
+    return -1;
+  const int kblocks = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int cps = p.ci_chunks * p.co_chunks;
+  if (splits <= 0) {
+    splits = g_num_sms / cps;                 // one wave
+    if (splits < 1) splits = 1;
+  }
+  if (splits > kblocks) splits = kblocks;
+  {
+    const int per = (kblocks + splits - 1) / splits;
+    splits = (kblocks + per - 1) / per;
+  }
+  p.splits = splits;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         WH_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);
+    attr_set = true;
+  }
+  int grid = cps * splits;
+  if (grid > g_num_sms) grid = g_num_sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  conv_wgrad_halo_kernel<<<grid, NUM_THREADS, WH_SMEM_BYTES, st>>>(mx, my, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(cudaGetErrorString(e), (int)e);
+  return 0;
+}
+
 void init_gemm_params(GemmParams& g) {
   memset(&g, 0, sizeof(g));
   g.M = INT_MAX;
@@ -844,6 +1086,8 @@ int b200dp_conv_wgrad(const void* dy, const void* x, void* dw_acc, int N, int H,
   ConvShape s{N, H, W, Cin, Cout, R, S, stride, pad, 0, 0};
   if (check_shape(s)) return -1;
   if (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dw_acc) & 15) return fail("pointers must be 16-byte aligned");
+  if (halo_enabled() && R == 3 && stride == 1 && W >= 7 && H >= 7 && block_n == 0)
+    return launch_wgrad_halo(dy, x, dw_acc, s, splits, max_ctas, (cudaStream_t)(uintptr_t)stream);
   const int BN = pick_bn(Cin, block_n);
   ConvMaps maps;
   ConvParams p;
@@ -872,7 +1116,8 @@ int b200dp_conv_wgrad(const void* dy, const void* x, void* dw_acc, int N, int H,
     }
   const int tiles = p.g.num_m_blocks * p.g.num_n_blocks * R * S;
   if (splits <= 0) {
-    splits = (g_num_sms + tiles - 1) / tiles;            // one wave: every extra split costs a tile of REDs
+    splits = g_num_sms / tiles;                          // one wave (148 SMs): never a second, short one
+    if (splits < 1) splits = 1;
     const int max_splits = kblocks / 8 > 1 ? kblocks / 8 : 1;
     if (splits > max_splits) splits = max_splits;
   }
