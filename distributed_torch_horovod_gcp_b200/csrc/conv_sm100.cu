@@ -983,7 +983,9 @@ int b200dp_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W
       }
       t.wcol = (r * S + c) * Cin;
     }
-  const bool halo = halo_enabled() && R == 3 && stride == 1 && s.OH >= 12 && s.OW >= 8;
+  // measured (benchmarks/conv_bench.py): the halo tile's 8 x 16 shape wastes up to 30 % of the MMAs on 28/14-pixel
+  // maps, which only pays while the kernel is operand-fetch bound, i.e. for narrow N tiles
+  const bool halo = halo_enabled() && R == 3 && stride == 1 && s.OH >= 12 && s.OW >= 8 && Cout <= 128;
   if (halo) {
     if (setup_halo(maps, p, x, Cin, W, H, N)) return -1;
   } else if (stride == 1) {
@@ -1025,7 +1027,7 @@ int b200dp_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int
   choose_box(s.OW, s.OH, N, BLOCK_M, &p.bw, &p.bh, &p.bn);   // stride 2: each dx parity view is OW x OH
   p.tiles_w = (s.OW + p.bw - 1) / p.bw; p.tiles_h = (s.OH + p.bh - 1) / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
   p.num_taps_total = R * S;
-  const bool halo = halo_enabled() && R == 3 && s.OH >= 12 && s.OW >= 8;
+  const bool halo = halo_enabled() && R == 3 && stride == 1 && s.OH >= 12 && s.OW >= 8 && Cin <= 128;
   if (halo) { p.bw = HALO_BW; p.bh = HALO_BH; p.bn = 1; }
   int sw, sh, sn;
   slab_box(p.bw, p.bh, p.bn, &sw, &sh, &sn);
@@ -1086,7 +1088,7 @@ int b200dp_conv_wgrad(const void* dy, const void* x, void* dw_acc, int N, int H,
   ConvShape s{N, H, W, Cin, Cout, R, S, stride, pad, 0, 0};
   if (check_shape(s)) return -1;
   if (((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dw_acc) & 15) return fail("pointers must be 16-byte aligned");
-  if (halo_enabled() && R == 3 && stride == 1 && W >= 7 && H >= 7 && block_n == 0)
+  if (halo_enabled() && R == 3 && stride == 1 && W >= 7 && H >= 7 && block_n == 0 && (long)Cin * Cout <= 65536)
     return launch_wgrad_halo(dy, x, dw_acc, s, splits, max_ctas, (cudaStream_t)(uintptr_t)stream);
   const int BN = pick_bn(Cin, block_n);
   ConvMaps maps;
