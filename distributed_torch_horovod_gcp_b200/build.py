@@ -4,7 +4,7 @@
 
 Produces ``distributed_torch_horovod_gcp_b200/lib/*.so`` for sm_100a:
   libb200dp_comm.so     csrc/runtime.cpp + csrc/comm_kernels.cu
-  libb200dp_kernels.so  csrc/gemm_sm100.cu, csrc/elementwise.cu, csrc/lstm_kernels.cu ...
+  libb200dp_kernels.so  csrc/gemm_sm100.cu, conv_sm100.cu, elementwise.cu, lstm_kernels.cu, lstm_rec_sm100.cu ...
 nvcc cross-compiles without a GPU, so this also runs on the CPU dev box.
 """
 from __future__ import annotations
@@ -28,7 +28,8 @@ NVCC_FLAGS = [
 
 TARGETS = {
     "libb200dp_comm.so": ["runtime.cpp", "comm_kernels.cu"],
-    "libb200dp_kernels.so": ["gemm_sm100.cu", "conv_sm100.cu", "elementwise.cu", "lstm_kernels.cu"],
+    "libb200dp_kernels.so": ["gemm_sm100.cu", "conv_sm100.cu", "elementwise.cu", "lstm_kernels.cu",
+                             "lstm_rec_sm100.cu"],
 }
 
 

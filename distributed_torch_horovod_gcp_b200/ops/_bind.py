@@ -9,6 +9,8 @@ from . import bn as _bn
 from . import lstm_fused as _lstm
 from . import ln as _ln
 from . import conv as _conv
+from . import lstm_rec as _lstm_rec
+from .lstm_rec import lstm_recurrent  # noqa: F401
 from .conv import conv3x3, conv2d as conv2d_implicit  # noqa: F401
 from .ln import layer_norm  # noqa: F401
 from .gemm import linear, mlp, qkv_proj  # noqa: F401  (re-exported as kernels.linear / .mlp / .qkv_proj)
@@ -21,6 +23,7 @@ def register(lib, have: Dict[str, bool]) -> None:
     _lstm.register(lib, have)
     _ln.register(lib, have)
     _conv.register(lib, have)
+    _lstm_rec.register(lib, have)
 
 
 def linear_supported(x, weight) -> bool:

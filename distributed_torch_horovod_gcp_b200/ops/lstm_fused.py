@@ -1,7 +1,7 @@
 """K6 — fused linear head of the reference LSTM model (csrc/lstm_kernels.cu): the last-timestep
 gather (reference index_select, app/torch_train.py:196) + the three activation-free linears
 (app/torch_train.py:199-205) as ONE forward kernel and TWO backward kernels, fp32.  The recurrent
-part stays on cuDNN this round (K5: see DESIGN.md §4 for the tcgen05/cluster plan)."""
+part is the persistent cluster kernel K5 (ops/lstm_rec.py, csrc/lstm_rec_sm100.cu)."""
 from __future__ import annotations
 
 import ctypes
@@ -89,8 +89,15 @@ def available(model, x: torch.Tensor) -> bool:
 
 
 def forward(model, x, hidden):
-    """cuDNN recurrent part + fused head (K6)."""
-    seq, model.hidden = model.lstm(x, hidden)
+    """Persistent recurrence kernel (K5, ops/lstm_rec.py; cuDNN only for shapes it does not cover)
+    + fused head (K6)."""
+    from . import lstm_rec
+    lstm = model.lstm
+    if model.n_layers == 1 and lstm_rec.supported(x, lstm.weight_hh_l0):
+        seq, model.hidden = lstm_rec.lstm_recurrent(x, hidden[0], hidden[1], lstm.weight_ih_l0,
+                                                    lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)
+    else:
+        seq, model.hidden = lstm(x, hidden)
     if not seq.is_contiguous():
         seq = seq.contiguous()
     return _HeadFn.apply(seq, model.window_size - 1, model.linear.weight, model.linear.bias,
