@@ -69,7 +69,23 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, float a, float b, f
 __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// generic-proxy writes to shared memory (local CTA / any CTA of the cluster) -> visible to the async proxy
+// (tcgen05.mma operand reads).  The state-space qualified forms are far cheaper than the full
+// `fence.proxy.async` (which ptxas expands to MEMBAR.ALL.CTA + ERRBAR + FENCE.VIEW.ASYNC).
+__device__ __forceinline__ void fence_proxy_async_all() {
+  asm volatile("fence.proxy.async.shared::cluster;" ::: "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float a) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -169,12 +185,28 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_rec_fwd_kernel(const RecFwdP
   const uint32_t c = my_cluster_rank();
   const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
 
-  // ---- resident A operand: W_hh rows {g*256 + 32c + j}, K-major tf32, 128B swizzle
-  for (int i = tid; i < 128 * 64; i += LTHREADS) {
-    const int r = i >> 6, k4 = i & 63;
-    const int grow = (r >> 5) * LH + (int)c * LU + (r & 31);
-    const float4 v = *reinterpret_cast<const float4*>(p.w_hh + (size_t)grow * LH + k4 * 4);
-    *reinterpret_cast<float4*>(sA + sw_off(r, k4 * 4, 128)) = v;
+  // ---- resident A operand: W_hh rows {g*256 + 32c + j}, K-major tf32, 128B swizzle.  Loads are issued in
+  // batches of 8 independent 128-bit requests per thread before any store (latency-bound otherwise).
+  {
+    const uint32_t sA_u = smem_u32(sA);
+    constexpr int TOTAL = 128 * 64, BATCH = 8;
+    for (int base = tid; base < TOTAL; base += LTHREADS * BATCH) {
+      float4 v[BATCH];
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int i = base + u * LTHREADS;
+        if (i < TOTAL) {
+          const int r = i >> 6, k4 = i & 63;
+          const int grow = (r >> 5) * LH + (int)c * LU + (r & 31);
+          v[u] = __ldg(reinterpret_cast<const float4*>(p.w_hh + (size_t)grow * LH + k4 * 4));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int i = base + u * LTHREADS;
+        if (i < TOTAL) sts_v4(sA_u + sw_off(i >> 6, (i & 63) * 4, 128), v[u].x, v[u].y, v[u].z, v[u].w);
+      }
+    }
   }
   if (tid == 0) {
     mbar_init(mma_done, 1);
@@ -201,7 +233,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_rec_fwd_kernel(const RecFwdP
       const int b = i >> 6, k4 = i & 63;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (b0 + b < p.B) v = *reinterpret_cast<const float4*>(p.h0 + (size_t)(b0 + b) * LH + k4 * 4);
-      *reinterpret_cast<float4*>(sB + sw_off(b, k4 * 4, NB)) = v;
+      sts_v4(smem_u32(sB) + sw_off(b, k4 * 4, NB), v.x, v.y, v.z, v.w);
     }
     float cstate[8], hlast[8];
     const int ju = lane;                       // unit owned by this thread in the cell update
@@ -260,11 +292,11 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_rec_fwd_kernel(const RecFwdP
           for (int b = 0; b < NB; ++b)
             if (b0 + b < p.B) p.gates[((size_t)t * p.B + b0 + b) * LG + grow] = v[b];
         }
-        float* gx = reinterpret_cast<float*>(sG);
+        const uint32_t gx = smem_u32(sG);
 #pragma unroll
         for (int cb = 0; cb < 8; ++cb)
-          *reinterpret_cast<float4*>(gx + (warp * 32 + lane) * 32 + ((cb ^ (lane & 7)) << 2)) =
-              make_float4(v[4 * cb], v[4 * cb + 1], v[4 * cb + 2], v[4 * cb + 3]);
+          sts_v4(gx + (uint32_t)(((warp * 32 + lane) * 32 + ((cb ^ (lane & 7)) << 2)) * 4), v[4 * cb], v[4 * cb + 1],
+                 v[4 * cb + 2], v[4 * cb + 3]);
         tc_fence_before();
         epi_barrier();
         // ---- cell update for (unit ju, batch bb .. bb+7)
@@ -273,10 +305,10 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_rec_fwd_kernel(const RecFwdP
         for (int h2 = 0; h2 < 2; ++h2) {
           const int cb = (bb >> 2) + h2;
           const int pos = ((cb ^ (ju & 7)) << 2);
-          const float4 vi = *reinterpret_cast<const float4*>(gx + (0 * 32 + ju) * 32 + pos);
-          const float4 vf = *reinterpret_cast<const float4*>(gx + (1 * 32 + ju) * 32 + pos);
-          const float4 vg = *reinterpret_cast<const float4*>(gx + (2 * 32 + ju) * 32 + pos);
-          const float4 vo = *reinterpret_cast<const float4*>(gx + (3 * 32 + ju) * 32 + pos);
+          const float4 vi = lds_v4(gx + (uint32_t)(((0 * 32 + ju) * 32 + pos) * 4));
+          const float4 vf = lds_v4(gx + (uint32_t)(((1 * 32 + ju) * 32 + pos) * 4));
+          const float4 vg = lds_v4(gx + (uint32_t)(((2 * 32 + ju) * 32 + pos) * 4));
+          const float4 vo = lds_v4(gx + (uint32_t)(((3 * 32 + ju) * 32 + pos) * 4));
           gi[4 * h2] = vi.x; gi[4 * h2 + 1] = vi.y; gi[4 * h2 + 2] = vi.z; gi[4 * h2 + 3] = vi.w;
           gf[4 * h2] = vf.x; gf[4 * h2 + 1] = vf.y; gf[4 * h2 + 2] = vf.z; gf[4 * h2 + 3] = vf.w;
           gg[4 * h2] = vg.x; gg[4 * h2 + 1] = vg.y; gg[4 * h2 + 2] = vg.z; gg[4 * h2 + 3] = vg.w;
@@ -334,14 +366,14 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_rec_fwd_kernel(const RecFwdP
 // backward recurrence
 // ---------------------------------------------------------------------------------------------------
 struct RecBwdParams {
-  const float* w_hh;    // [1024][256]
-  const float* gates;   // [T][B][1024]
-  const float* cs;      // [T][B][256]
-  const float* c0;      // [B][256]
-  const float* dseq;    // [B][T][256]   (may be nullptr)
-  const float* dhT;     // [B][256]      (may be nullptr)
-  const float* dcT;     // [B][256]      (may be nullptr)
-  float* dgates;        // [T][B][1024]
+  const float* __restrict__ w_hh;    // [1024][256]
+  const float* __restrict__ gates;   // [T][B][1024]
+  const float* __restrict__ cs;      // [T][B][256]
+  const float* __restrict__ c0;      // [B][256]
+  const float* __restrict__ dseq;    // [B][T][256]   (may be nullptr)
+  const float* __restrict__ dhT;     // [B][256]      (may be nullptr)
+  const float* __restrict__ dcT;     // [B][256]      (may be nullptr)
+  float* __restrict__ dgates;        // [T][B][1024]
   float* dh0;           // [B][256]
   float* dc0;           // [B][256]
   int B, T;
@@ -366,11 +398,33 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_rec_bwd_kernel(const RecBwdP
   const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
 
   // ---- resident A operand: (W_slice)^T, rows = k (256), K = local gate row r (128), K-major, swizzled.
-  // Read W rows coalesced (k fastest) and scatter: a one-time 128 KB transpose per launch.
-  for (int i = tid; i < 128 * LH; i += LTHREADS) {
-    const int r = i >> 8, k = i & 255;
-    const int grow = (r >> 5) * LH + (int)c * LU + (r & 31);
-    *reinterpret_cast<float*>(sA + sw_off(k, r, LH)) = p.w_hh[(size_t)grow * LH + k];
+  // W rows are read coalesced (128-bit, 8 requests in flight per thread) and scattered transposed.
+  {
+    const uint32_t sA_u = smem_u32(sA);
+    constexpr int TOTAL = 128 * 64, BATCH = 8;
+    for (int base = tid; base < TOTAL; base += LTHREADS * BATCH) {
+      float4 v[BATCH];
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int i = base + u * LTHREADS;
+        if (i < TOTAL) {
+          const int r = i >> 6, k4 = i & 63;
+          const int grow = (r >> 5) * LH + (int)c * LU + (r & 31);
+          v[u] = __ldg(reinterpret_cast<const float4*>(p.w_hh + (size_t)grow * LH + k4 * 4));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {
+        const int i = base + u * LTHREADS;
+        if (i < TOTAL) {
+          const int r = i >> 6, k = (i & 63) * 4;
+          sts_f32(sA_u + sw_off(k + 0, r, LH), v[u].x);
+          sts_f32(sA_u + sw_off(k + 1, r, LH), v[u].y);
+          sts_f32(sA_u + sw_off(k + 2, r, LH), v[u].z);
+          sts_f32(sA_u + sw_off(k + 3, r, LH), v[u].w);
+        }
+      }
+    }
   }
   if (tid == 0) {
     mbar_init(mma_done, 1);
@@ -409,25 +463,38 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_rec_bwd_kernel(const RecBwdP
       const int cur = (p.T - 1 - t) & 1;        // reduce buffer written during this step
       if (warp < 4) {
         // ---- dgates for (unit ju, batch bb..bb+7)
-        float* sBf = reinterpret_cast<float*>(sB);
+        const uint32_t sB_u = smem_u32(sB);
+        // all global operands of the 8 batch rows first (one memory round trip instead of eight)
+        float gi[8], gf[8], gg[8], go[8], ct[8], cprev[8], dsq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int b = b0 + bb + i;
+          const bool ok = b < p.B;
+          const size_t gbase = ((size_t)t * p.B + (ok ? b : 0)) * LG + kglob;
+          gi[i] = ok ? __ldg(p.gates + gbase) : 0.f;
+          gf[i] = ok ? __ldg(p.gates + gbase + LH) : 0.f;
+          gg[i] = ok ? __ldg(p.gates + gbase + 2 * LH) : 0.f;
+          go[i] = ok ? __ldg(p.gates + gbase + 3 * LH) : 0.f;
+          ct[i] = ok ? __ldg(p.cs + ((size_t)t * p.B + b) * LH + kglob) : 0.f;
+          cprev[i] = !ok ? 0.f
+                         : ((t > 0) ? __ldg(p.cs + ((size_t)(t - 1) * p.B + b) * LH + kglob)
+                                    : __ldg(p.c0 + (size_t)b * LH + kglob));
+          dsq[i] = (ok && p.dseq != nullptr) ? __ldg(p.dseq + ((size_t)b * p.T + t) * LH + kglob) : 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int b = b0 + bb + i;
           float di = 0.f, df = 0.f, dg = 0.f, dob = 0.f;
           if (b < p.B) {
             const size_t gbase = ((size_t)t * p.B + b) * LG + kglob;
-            const float gi = p.gates[gbase], gf = p.gates[gbase + LH], gg = p.gates[gbase + 2 * LH],
-                        go = p.gates[gbase + 3 * LH];
-            const float ct = p.cs[((size_t)t * p.B + b) * LH + kglob];
-            const float cprev = (t > 0) ? p.cs[((size_t)(t - 1) * p.B + b) * LH + kglob] : p.c0[(size_t)b * LH + kglob];
-            const float dh = dh_rec[i] + (p.dseq != nullptr ? p.dseq[((size_t)b * p.T + t) * LH + kglob] : 0.f);
-            const float tc = tanhf_fast(ct);
-            const float dc = dc_next[i] + dh * go * (1.0f - tc * tc);
-            dob = dh * tc * go * (1.0f - go);
-            di = dc * gg * gi * (1.0f - gi);
-            df = dc * cprev * gf * (1.0f - gf);
-            dg = dc * gi * (1.0f - gg * gg);
-            dc_next[i] = dc * gf;
+            const float dh = dh_rec[i] + dsq[i];
+            const float tc = tanhf_fast(ct[i]);
+            const float dc = dc_next[i] + dh * go[i] * (1.0f - tc * tc);
+            dob = dh * tc * go[i] * (1.0f - go[i]);
+            di = dc * gg[i] * gi[i] * (1.0f - gi[i]);
+            df = dc * cprev[i] * gf[i] * (1.0f - gf[i]);
+            dg = dc * gi[i] * (1.0f - gg[i] * gg[i]);
+            dc_next[i] = dc * gf[i];
             p.dgates[gbase] = di;
             p.dgates[gbase + LH] = df;
             p.dgates[gbase + 2 * LH] = dg;
@@ -436,10 +503,10 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_rec_bwd_kernel(const RecBwdP
             dc_next[i] = 0.f;
           }
           // B operand: rows = batch, K = local gate row (g*32 + ju)
-          *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sBf) + sw_off(bb + i, 0 * 32 + ju, NB)) = di;
-          *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sBf) + sw_off(bb + i, 1 * 32 + ju, NB)) = df;
-          *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sBf) + sw_off(bb + i, 2 * 32 + ju, NB)) = dg;
-          *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sBf) + sw_off(bb + i, 3 * 32 + ju, NB)) = dob;
+          sts_f32(sB_u + sw_off(bb + i, 0 * 32 + ju, NB), di);
+          sts_f32(sB_u + sw_off(bb + i, 1 * 32 + ju, NB), df);
+          sts_f32(sB_u + sw_off(bb + i, 2 * 32 + ju, NB), dg);
+          sts_f32(sB_u + sw_off(bb + i, 3 * 32 + ju, NB), dob);
         }
       }
       fence_proxy_async_all();
@@ -488,13 +555,13 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_rec_bwd_kernel(const RecBwdP
       tc_fence_after();
       if (warp < 4) {
         // dh_{t-1}[unit ju][batch bb..bb+7] = sum over the 8 source CTAs
-        const float* red = reinterpret_cast<const float*>(sR + cur * BW_R_BYTES);
+        const uint32_t red = smem_u32(sR + cur * BW_R_BYTES);
 #pragma unroll
         for (int i = 0; i < 8; ++i) dh_rec[i] = 0.f;
 #pragma unroll
         for (int s = 0; s < CL; ++s) {
-          const float4 v0 = *reinterpret_cast<const float4*>(red + (s * 32 + ju) * 32 + bb);
-          const float4 v1 = *reinterpret_cast<const float4*>(red + (s * 32 + ju) * 32 + bb + 4);
+          const float4 v0 = lds_v4(red + (uint32_t)(((s * 32 + ju) * 32 + bb) * 4));
+          const float4 v1 = lds_v4(red + (uint32_t)(((s * 32 + ju) * 32 + bb + 4) * 4));
           dh_rec[0] += v0.x; dh_rec[1] += v0.y; dh_rec[2] += v0.z; dh_rec[3] += v0.w;
           dh_rec[4] += v1.x; dh_rec[5] += v1.y; dh_rec[6] += v1.z; dh_rec[7] += v1.w;
         }
