@@ -290,53 +290,52 @@ def run_arm(impl, wl, hvd, world, rank, steps, warmup, graph_mode, want_e2e, wan
 
 
 def selfcheck(wl, hvd, world, rank):
-    """One training step through the fused engine vs dist.all_reduce + torch optimizer on a clone
-    (both on this repo's kernels, same per-rank input), plus cross-rank bit-equality of the result."""
+    """Reduction + update check at N > 1, with IDENTICAL local gradients on both arms: one backward on
+    a plain clone produces per-rank gradients; (a) ``dist.all_reduce`` (NCCL) average + the stock torch
+    optimizer update the clone, (b) the same local gradients are placed in the fused engine's gradient
+    buckets and ONE fused sm_100a launch per bucket reduces them over NVLink and updates the model.
+    Also checks that the updated replicas are bit-identical across ranks."""
     import copy
     import hashlib
     import torch
     import torch.distributed as dist
     os.environ.setdefault("B200DP_FUSED_SINGLE", "1")
     model = wl.build_model(seed=99)
-    ref = copy.deepcopy(model)
     opt = hvd.DistributedOptimizer(wl.build_optimizer(model), named_parameters=model.named_parameters())
     hvd.broadcast_parameters(model.state_dict(), root_rank=0)
-    with torch.no_grad():
-        for p, q in zip(ref.parameters(), model.parameters()):
-            p.copy_(q)
-        for p, q in zip(ref.buffers(), model.buffers()):
-            p.copy_(q)
+    ref = copy.deepcopy(model)
+    for p in ref.parameters():
+        p.grad = None
+        if hasattr(p, "_b200dp_sink"):
+            del p._b200dp_sink
     ropt = wl.build_optimizer(ref)
     x, y = wl.data().next()
-    if wl.is_lstm:           # the model draws random (h0, c0) per forward: same stream for both passes
-        torch.manual_seed(7 + rank)
-    wl.loss(model(x), y).backward()
-    opt.step()
+    wl.loss(ref(x), y).backward()                      # local gradients (plain autograd accumulation)
+    with torch.no_grad():
+        for p, q in zip(model.parameters(), ref.parameters()):
+            p.grad.copy_(q.grad)                       # same bits into the fused engine's buckets
+    opt.step()                                         # synchronize(): every bucket launched once
     opt.zero_grad()
-    if wl.is_lstm:
-        torch.manual_seed(7 + rank)
-    wl.loss(ref(x), y).backward()
     for p in ref.parameters():
-        if p.grad is not None:
-            g = p.grad.float()
-            dist.all_reduce(g)
-            p.grad.copy_((g / world).to(p.grad.dtype))
+        g = p.grad.float()
+        dist.all_reduce(g)
+        p.grad.copy_((g / world).to(p.grad.dtype))
     ropt.step()
     torch.cuda.synchronize()
-    num = den = 0.0
+    worst = 0.0
     for p, q in zip(model.parameters(), ref.parameters()):
-        # compare the UPDATE (what the step changed), relative to its own size
-        num = max(num, float((p.detach().float() - q.detach().float()).abs().max()))
-        den = max(den, float(q.detach().float().abs().max()))
+        a, b = p.detach().float(), q.detach().float()
+        worst = max(worst, float((a - b).abs().max() / b.abs().max().clamp_min(1e-12)))
     h = hashlib.sha256()
     for p in model.parameters():
         h.update(p.detach().contiguous().view(torch.uint8).cpu().numpy().tobytes())
     digests = hvd.allgather_object(h.hexdigest())
     opt.remove_hooks()
-    return {"max_abs_err_vs_allreduce_plus_torch_optimizer": num, "max_abs_param": den,
-            "max_rel_err": num / max(den, 1e-12), "replicas_bit_identical": len(set(digests)) == 1,
-            "note": "bf16 models: the torch reference updates bf16 parameters in bf16 while the fused "
-                    "engine keeps fp32 masters, and BN batch statistics use fp32 atomics"}
+    return {"max_rel_err": worst, "replicas_bit_identical": len(set(digests)) == 1,
+            "expected": ("<= 2^-8 (one bf16 ulp: torch updates bf16 parameters in bf16, the fused engine "
+                         "rounds fp32 masters once)" if wl.dtype_name == "bf16" else "fp32 rounding (~1e-6)"),
+            "what": "fused NVLink allreduce+update vs NCCL all_reduce + torch optimizer on identical "
+                    "local gradients; per-tensor max|a-b| / max|b|, worst tensor"}
 
 
 def main():
