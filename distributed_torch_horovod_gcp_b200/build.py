@@ -29,7 +29,7 @@ NVCC_FLAGS = [
 TARGETS = {
     "libb200dp_comm.so": ["runtime.cpp", "comm_kernels.cu"],
     "libb200dp_kernels.so": ["gemm_sm100.cu", "conv_sm100.cu", "elementwise.cu", "lstm_kernels.cu",
-                             "lstm_rec_sm100.cu"],
+                             "lstm_rec_sm100.cu", "attn_sm100.cu"],
 }
 
 

@@ -10,6 +10,8 @@ from . import lstm_fused as _lstm
 from . import ln as _ln
 from . import conv as _conv
 from . import lstm_rec as _lstm_rec
+from . import attention as _attn
+from .attention import attention_fused  # noqa: F401
 from .lstm_rec import lstm_recurrent  # noqa: F401
 from .conv import conv3x3, conv2d as conv2d_implicit  # noqa: F401
 from .ln import layer_norm  # noqa: F401
@@ -24,6 +26,7 @@ def register(lib, have: Dict[str, bool]) -> None:
     _ln.register(lib, have)
     _conv.register(lib, have)
     _lstm_rec.register(lib, have)
+    _attn.register(lib, have)
 
 
 def linear_supported(x, weight) -> bool:

@@ -117,6 +117,11 @@ def qkv_attention(x, weight, bias, heads: int):
         hd = D // heads
         q, kk, v = k.qkv_proj(x, weight, bias)
         q, kk, v = [t.view(B, S, heads, hd).transpose(1, 2) for t in (q, kk, v)]
+        if k.has("attention_fused") and hd == 64 and os.environ.get("B200DP_ATTN_KERNEL", "1") == "1":
+            from . import attention as _attn
+            if _attn.supported(q, kk, v):
+                o = _attn.attention_fused(q, kk, v)       # [B,H,S,hd] view of [B,S,H,hd] memory
+                return o.transpose(1, 2).reshape(B, S, D)  # a view: no copy
         o = F.scaled_dot_product_attention(q, kk, v)
         return o.transpose(1, 2).reshape(B, S, D)
     return attention(linear(x, weight, bias), heads)
