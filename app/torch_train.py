@@ -103,7 +103,8 @@ if __name__ == "__main__":
     compute_dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
 
     if is_lstm:
-        df, source = ensure_dataset(args.data, rank=hvd.rank())
+        df, source = ensure_dataset(args.data, rank=hvd.rank(),
+                                    decide=(lambda v: hvd.broadcast_object(v, 0)) if hvd.size() > 1 else None)
         if hvd.size() > 1:
             hvd.barrier()
         x_train, x_test, y_train, y_test, scaler = reshape_and_scale_data_for_training(

@@ -15,6 +15,7 @@ reference app/torch_train.py:210,217,227,232).  Design differences, B200-first:
 from __future__ import annotations
 
 import datetime
+import logging
 import os
 import threading
 from dataclasses import dataclass, field
@@ -22,6 +23,8 @@ from typing import Optional
 
 import torch
 import torch.distributed as dist
+
+log = logging.getLogger("b200dp")
 
 
 def _env_int(*names: str, default: Optional[int] = None) -> Optional[int]:
@@ -121,6 +124,17 @@ def init(comm=None, process_sets=None) -> None:
             except Exception:
                 rt.cpu_group = dist.group.WORLD
         rt.initialized = True
+        lvl = os.environ.get("HOROVOD_LOG_LEVEL") or os.environ.get("B200DP_LOG_LEVEL")
+        if lvl:      # horovodrun --log-level: TRACE/DEBUG/INFO/WARNING/ERROR/FATAL -> the package logger
+            lv = {"TRACE": logging.DEBUG, "FATAL": logging.CRITICAL}.get(lvl.upper(),
+                                                                         getattr(logging, lvl.upper(), None))
+            if lv is not None:
+                log.setLevel(lv)
+                if not log.handlers:
+                    h = logging.StreamHandler()
+                    h.setFormatter(logging.Formatter(f"[b200dp rank {rank}] %(levelname)s %(message)s"))
+                    log.addHandler(h)
+        log.debug("init: rank %d/%d local %d/%d", rank, size, local_rank, local_size)
         tl = os.environ.get("HOROVOD_TIMELINE") or os.environ.get("B200DP_TIMELINE")
         if tl:
             from .utils.timeline import Timeline
@@ -137,6 +151,12 @@ def shutdown() -> None:
                 rt.timeline.close()
             finally:
                 rt.timeline = None
+        try:      # engines hold views of symmetric arenas: detach the models before unmapping
+            from .parallel.fused_engine import live_engines
+            for eng in live_engines():
+                eng.release()
+        except Exception:
+            pass
         if rt.symm is not None:
             try:
                 rt.symm.close()
@@ -224,4 +244,11 @@ def get_symm(device: Optional[torch.device] = None):
                 "); CUDA collectives FALL BACK to NCCL — this is not the product path.")
         return None
     rt.symm = symm
+    if os.environ.get("HOROVOD_AUTOTUNE", "0") == "1":
+        from .runtime import tuning
+        try:
+            res = tuning.autotune(symm)
+            log.info("autotune: world %d -> %s", rt.size, res["table"])
+        except Exception as e:  # noqa: BLE001 - keep the static table
+            log.warning("autotune failed (%s); using the built-in algorithm table", e)
     return symm

@@ -295,22 +295,31 @@ struct AttnBwdParams {
   long long dk_sb, dk_sh, dk_ss, dv_sb, dv_sh, dv_ss;
 };
 
-// delta[b][h][s] = sum_d dO * O   (one warp per row)
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
-                                  float* __restrict__ delta, int B, int H, int S, long long o_sb, long long o_sh,
-                                  long long o_ss, long long d_sb, long long d_sh, long long d_ss) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= (long long)B * H * S) return;
-  const int s = (int)(row % S);
-  const int h = (int)((row / S) % H);
-  const int b = (int)(row / ((long long)S * H));
-  const __nv_bfloat162 ov = *reinterpret_cast<const __nv_bfloat162*>(o + b * o_sb + h * o_sh + s * o_ss + lane * 2);
-  const __nv_bfloat162 dv = *reinterpret_cast<const __nv_bfloat162*>(dout + b * d_sb + h * d_sh + s * d_ss + lane * 2);
-  float v = __bfloat162float(ov.x) * __bfloat162float(dv.x) + __bfloat162float(ov.y) * __bfloat162float(dv.y);
+// delta[b][h][s] = sum_d dO * O   (8 lanes per row: one 16-byte load of each tensor per lane)
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
+                                                         const __nv_bfloat16* __restrict__ dout,
+                                                         float* __restrict__ delta, int B, int H, int S, long long o_sb,
+                                                         long long o_sh, long long o_ss, long long d_sb, long long d_sh,
+                                                         long long d_ss) {
+  const unsigned total = (unsigned)B * (unsigned)H * (unsigned)S;
+  const unsigned row = blockIdx.x * 32u + (threadIdx.x >> 3);
+  const int sub = threadIdx.x & 7;
+  float v = 0.f;
+  if (row < total) {
+    const unsigned s = row % (unsigned)S;
+    const unsigned bh = row / (unsigned)S;
+    const unsigned h = bh % (unsigned)H, b = bh / (unsigned)H;
+    const uint4 ov = *reinterpret_cast<const uint4*>(o + b * o_sb + h * o_sh + s * o_ss + sub * 8);
+    const uint4 dv = *reinterpret_cast<const uint4*>(dout + b * d_sb + h * d_sh + s * d_ss + sub * 8);
+    float a[8], c[8];
+    unpack8(ov, a);
+    unpack8(dv, c);
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-  if (lane == 0) delta[row] = v;
+    for (int i = 0; i < 8; ++i) v = fmaf(a[i], c[i], v);
+  }
+#pragma unroll
+  for (int off = 4; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (sub == 0 && row < total) delta[row] = v;
 }
 
 // smem: K_j, V_j (resident), ring of 2 x {Q_i, dO_i}, P (32 KB), dS (32 KB)
@@ -403,24 +412,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
       const uint32_t id_t = idesc_bf16(HD, true, true);          // P^T dO / dS^T Q : M = keys (MN-major A), N = d
       const uint32_t id_q = idesc_bf16(HD, false, true);         // dS K : A K-major (K = keys), B MN-major
       mbar_wait(kv_full, 0);
-      for (int i = 0; i < nq; ++i) {
+      auto issue_sdp = [&](int i) {
         const int st = i % BW_RING;
-        const uint32_t sQ_u = smem_u32(sR + (2 * st) * TILE_BYTES), sO_u = sQ_u + TILE_BYTES;
+        const uint32_t sQ_u = smem_u32(sR + (2 * st) * TILE_BYTES);
         mbar_wait(&r_full[st], (i / BW_RING) & 1);
-        if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);             // softmax warps finished with S/dP/dQ of tile i-1
         tc_fence_after();
-        const uint64_t dQ_k = kmaj + desc_addr(sQ_u), dO_k = kmaj + desc_addr(sO_u);
+        const uint64_t dQ_k = kmaj + desc_addr(sQ_u), dO_k = kmaj + desc_addr(sQ_u + TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem + TM_S, dQ_k + 2 * k, dK_k + 2 * k, id_s, k ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) tc_mma_bf16(tmem + TM_DP, dO_k + 2 * k, dV_k + 2 * k, id_s, k ? 1u : 0u);
         tc_commit(sdp_full);
-        mbar_wait(pds_full, i & 1);
+      };
+      issue_sdp(0);
+      const uint64_t mn_a = make_desc_base(TILE_BYTES, 1024);   // P / dS: 64-key chunks are 128 rows (16 KB) apart
+      const uint64_t aP = mn_a + desc_addr(sP_u), aS = mn_a + desc_addr(sS_u);
+      for (int i = 0; i < nq; ++i) {
+        const int st = i % BW_RING;
+        const uint32_t sQ_u = smem_u32(sR + (2 * st) * TILE_BYTES), sO_u = sQ_u + TILE_BYTES;
+        mbar_wait(pds_full, i & 1);                               // P_i, dS_i in smem; S / dP TMEM free again
+        if (i > 0) mbar_wait(dq_empty, (i - 1) & 1);              // dQ_{i-1} drained from TMEM
         tc_fence_after();
         // dV += P^T dO_i ; dK += dS^T Q_i : A = P / dS read MN-major (M = keys contiguous, K = q rows),
         // chunk c (64 keys) at +c*TILE_BYTES; B = dO_i / Q_i MN-major (N = d, K = q rows)
-        const uint64_t mn_a = make_desc_base(TILE_BYTES, 1024);   // P / dS: 64-key chunks are 128 rows (16 KB) apart
-        const uint64_t aP = mn_a + desc_addr(sP_u), aS = mn_a + desc_addr(sS_u);
         const uint64_t bO = mnmaj + desc_addr(sO_u), bQ = mnmaj + desc_addr(sQ_u);
 #pragma unroll
         for (int k = 0; k < TILE / 16; ++k) tc_mma_bf16(tmem + TM_DV, aP + k * 128, bO + k * 128, id_t, (i | k) ? 1u : 0u);
@@ -433,6 +447,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant
         }
         tc_commit(&r_empty[st]);
         tc_commit(dq_full);
+        // next tile's S / dP go out now: their MMAs and the softmax that follows overlap the dQ_i drain.
+        // (P / dS smem is only rewritten after dq_full(i), i.e. after the MMAs above have read it.)
+        if (i + 1 < nq) issue_sdp(i + 1);
       }
       tc_commit(fin_full);
     }
@@ -620,7 +637,7 @@ int b200dp_attn_bwd(const void* q, const void* k, const void* v, const void* o, 
       make_qkv_map(&mv, v, B, H, S, vs[0], vs[1], vs[2]) || make_qkv_map(&mdo, dout, B, H, S, dos[0], dos[1], dos[2]))
     return -1;
   const long long rows = (long long)B * H * S;
-  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(
+  attn_delta_kernel<<<(unsigned)((rows + 31) / 32), 256, 0, st>>>(
       reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(dout), delta, B, H, S, os[0],
       os[1], os[2], dos[0], dos[1], dos[2]);
   AttnBwdParams p;

@@ -81,6 +81,19 @@ struct ARArgs {
   OptHyper h;
 };
 
+// reduce-scatter / all-gather / all-to-all over peer memory (equal chunks of `chunk` elements per rank)
+struct CollArgs {
+  const void* src[B200DP_MAX_RANKS];  // reduce-scatter: every rank's (symmetric) input; others: [rank] = local input
+  void* dst[B200DP_MAX_RANKS];        // all-gather / all-to-all: every rank's (symmetric) output; RS: [rank] = local out
+  const void* src_mc;                 // multicast VA of the inputs  (NVLS reduce-scatter)
+  void* dst_mc;                       // multicast VA of the outputs (NVLS all-gather)
+  unsigned long long chunk;           // elements per rank chunk (16-byte multiple)
+  float scale;
+  int channel;
+  int use_mc;
+  int pad_;
+};
+
 struct BcastArgs {
   void* buf[B200DP_MAX_RANKS];
   void* buf_mc;
@@ -155,7 +168,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // ------------------------------------------------------------------ cross-rank block barrier
 // Block b of every rank meets block b of every other rank.  acq_rel: writes made by this
 // block before the barrier (P2P / multimem stores) are visible to peers after it.
-__device__ __forceinline__ void rank_barrier(const CommCtx& c, int channel) {
+__device__ __forceinline__ bool rank_barrier(const CommCtx& c, int channel) {
+  __shared__ int s_failed;
+  if (threadIdx.x == 0) s_failed = 0;
   __syncthreads();
   const int t = threadIdx.x;
   if (c.world > 1 && t < c.world && t != c.rank) {
@@ -182,6 +197,7 @@ __device__ __forceinline__ void rank_barrier(const CommCtx& c, int channel) {
             mb[0] = 1;
             __threadfence_system();
           }
+          s_failed = 1;
           break;
         }
         __nanosleep(64);
@@ -189,7 +205,12 @@ __device__ __forceinline__ void rank_barrier(const CommCtx& c, int channel) {
     }
   }
   __syncthreads();
+  return s_failed == 0;
 }
+
+// After a watchdog expiry the data behind the barrier is incomplete: rank_barrier returns false and the
+// kernels return without reducing / writing anything (the host raises HorovodInternalError from the
+// mailbox) instead of producing silently wrong results.
 
 // ------------------------------------------------------------------ vector <-> fp32 helpers
 template <typename T>
@@ -398,7 +419,7 @@ __global__ void __launch_bounds__(512) allreduce_oneshot_kernel(CommCtx c, ARArg
   const StepInfo s = make_step(a);
   T* out_local = reinterpret_cast<T*>(a.copy_back ? a.scratch : a.out[c.rank]);
 
-  rank_barrier(c, a.channel);  // every peer's gradients are complete
+  if (!rank_barrier(c, a.channel)) return;  // every peer's gradients are complete
   for (size_t v = start; v < nvec; v += stride) {
     uint4 raw[B200DP_MAX_RANKS];
 #pragma unroll
@@ -440,7 +461,7 @@ __global__ void __launch_bounds__(512) allreduce_sliced_kernel(CommCtx c, ARArgs
   const size_t start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const StepInfo s = make_step(a);
 
-  rank_barrier(c, a.channel);
+  if (!rank_barrier(c, a.channel)) return;
   // U independent 16-byte transactions per thread are issued before any is consumed: NVLink
   // round trips are ~2 us, so bytes-in-flight (not instruction count) bounds the bandwidth.
   constexpr int U = kNVLS ? 4 : 2;
@@ -507,12 +528,111 @@ __global__ void __launch_bounds__(512) allreduce_sliced_kernel(CommCtx c, ARArgs
   finish_step(a);
 }
 
+// ------------------------------------------------------------------ reduce-scatter / all-gather / all-to-all
+// The two halves of the sliced allreduce as stand-alone collectives, plus the personalised exchange.
+// Reduce-scatter: rank r reads chunk r of every peer (P2P loads, or ONE multimem.ld_reduce per 16 bytes when
+// the switch does the sum) and keeps scale * sum locally — (N-1)/N * S bytes in per rank instead of the
+// 2 * S an allreduce-then-slice moves.  All-gather: rank r pushes its chunk into slot r of every peer
+// (one multimem.st per 16 bytes with NVLS).  All-to-all: rank r pushes chunk j into slot r of peer j.
+template <typename T, bool kNVLS>
+__global__ void __launch_bounds__(512) reducescatter_kernel(CommCtx c, CollArgs a) {
+  constexpr int VN = Vec<T>::N;
+  const size_t nvec = a.chunk / VN;
+  const size_t base = (size_t)c.rank * nvec;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint4* out = reinterpret_cast<uint4*>(a.dst[c.rank]);
+  if (!rank_barrier(c, a.channel)) return;
+  constexpr int U = kNVLS ? 4 : 2;
+  for (size_t v0 = start; v0 < nvec; v0 += U * stride) {
+    float acc[U][VN];
+    if (kNVLS) {
+      uint4 red[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t v = v0 + u * stride;
+        if (v < nvec) red[u] = Vec<T>::mc_reduce(reinterpret_cast<const uint4*>(a.src_mc) + base + v);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) Vec<T>::unpack(red[u], acc[u]);
+    } else {
+      uint4 raw[U][B200DP_MAX_RANKS];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t v = v0 + u * stride;
+#pragma unroll
+        for (int r = 0; r < B200DP_MAX_RANKS; ++r)
+          if (r < c.world && v < nvec) raw[u][r] = ld_peer_v4(reinterpret_cast<const uint4*>(a.src[r]) + base + v);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float f[VN];
+#pragma unroll
+        for (int i = 0; i < VN; ++i) acc[u][i] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < B200DP_MAX_RANKS; ++r) {   // fixed rank order
+          if (r < c.world) {
+            Vec<T>::unpack(raw[u][r], f);
+#pragma unroll
+            for (int i = 0; i < VN; ++i) acc[u][i] += f[i];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t v = v0 + u * stride;
+      if (v >= nvec) break;
+#pragma unroll
+      for (int i = 0; i < VN; ++i) acc[u][i] *= a.scale;
+      out[v] = Vec<T>::pack(acc[u]);
+    }
+  }
+  rank_barrier(c, a.channel);   // peers have finished reading my input
+}
+
+__global__ void __launch_bounds__(512) allgather_kernel(CommCtx c, CollArgs a) {
+  const size_t nvec = a.chunk;   // chunk is given in 16-byte vectors for the copy collectives
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(a.src[c.rank]);
+  const size_t slot = (size_t)c.rank * nvec;
+  if (!rank_barrier(c, a.channel)) return;   // every rank's output is free to overwrite
+  for (size_t v = start; v < nvec; v += stride) {
+    const uint4 x = src[v];
+    if (a.use_mc) {
+      mc_st_v4(reinterpret_cast<uint4*>(a.dst_mc) + slot + v, x);
+    } else {
+#pragma unroll
+      for (int r = 0; r < B200DP_MAX_RANKS; ++r)
+        if (r < c.world) st_peer_v4(reinterpret_cast<uint4*>(a.dst[r]) + slot + v, x);
+    }
+  }
+  rank_barrier(c, a.channel);   // all pushes visible everywhere
+}
+
+__global__ void __launch_bounds__(512) alltoall_kernel(CommCtx c, CollArgs a) {
+  const size_t nvec = a.chunk;   // 16-byte vectors per (source, destination) pair
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(a.src[c.rank]);
+  const size_t slot = (size_t)c.rank * nvec;
+  if (!rank_barrier(c, a.channel)) return;
+  for (int j = 0; j < c.world; ++j) {
+    const int peer = (c.rank + j) % c.world;          // staggered: no two ranks hammer the same peer first
+    uint4* dst = reinterpret_cast<uint4*>(a.dst[peer]) + slot;
+    const uint4* sp = src + (size_t)peer * nvec;
+    for (size_t v = start; v < nvec; v += stride) st_peer_v4(dst + v, sp[v]);
+  }
+  rank_barrier(c, a.channel);
+}
+
 // ------------------------------------------------------------------ K4: broadcast
 __global__ void __launch_bounds__(512) broadcast_kernel(CommCtx c, BcastArgs a) {
   const size_t nvec = a.nbytes / 16;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t start = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  rank_barrier(c, a.channel);  // destination buffers are free to overwrite on every rank
+  if (!rank_barrier(c, a.channel)) return;  // destination buffers are free to overwrite on every rank
   if (c.rank == a.root) {
     const uint4* src = reinterpret_cast<const uint4*>(a.buf[c.rank]);
     for (size_t v = start; v < nvec; v += stride) {
@@ -582,6 +702,48 @@ int b200dp_comm_allreduce(const CommCtx* ctx, const ARArgs* args, int algo, int 
   }
   return 0;
 }
+
+// mode: 0 reduce-scatter, 1 all-gather, 2 all-to-all.  dtype as in b200dp_comm_allreduce (reduce-scatter only).
+int b200dp_comm_collective(const CommCtx* ctx, const CollArgs* args, int mode, int dtype, int blocks, int threads,
+                           unsigned long long stream) {
+  if (blocks < 1 || blocks > B200DP_MAX_BLOCKS || threads < 32 || threads > 512 ||
+      args->channel < 0 || args->channel >= B200DP_NUM_CHANNELS) {
+    snprintf(g_comm_err, sizeof(g_comm_err), "bad launch config");
+    return -1;
+  }
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  if (mode == 0) {
+    const bool mc = args->use_mc != 0;
+    if (dtype == 0) {
+      if (mc) reducescatter_kernel<float, true><<<blocks, threads, 0, st>>>(*ctx, *args);
+      else reducescatter_kernel<float, false><<<blocks, threads, 0, st>>>(*ctx, *args);
+    } else if (dtype == 1) {
+      if (mc) reducescatter_kernel<__nv_bfloat16, true><<<blocks, threads, 0, st>>>(*ctx, *args);
+      else reducescatter_kernel<__nv_bfloat16, false><<<blocks, threads, 0, st>>>(*ctx, *args);
+    } else if (dtype == 2) {
+      if (mc) reducescatter_kernel<__half, true><<<blocks, threads, 0, st>>>(*ctx, *args);
+      else reducescatter_kernel<__half, false><<<blocks, threads, 0, st>>>(*ctx, *args);
+    } else {
+      snprintf(g_comm_err, sizeof(g_comm_err), "reduce-scatter: unsupported dtype %d", dtype);
+      return -1;
+    }
+  } else if (mode == 1) {
+    allgather_kernel<<<blocks, threads, 0, st>>>(*ctx, *args);
+  } else if (mode == 2) {
+    alltoall_kernel<<<blocks, threads, 0, st>>>(*ctx, *args);
+  } else {
+    snprintf(g_comm_err, sizeof(g_comm_err), "unknown collective mode %d", mode);
+    return -1;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_comm_err, sizeof(g_comm_err), "collective launch: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
+}
+
+int b200dp_comm_coll_bytes() { return (int)sizeof(CollArgs); }
 
 int b200dp_comm_broadcast(const CommCtx* ctx, const BcastArgs* args, int blocks, int threads,
                           unsigned long long stream) {

@@ -1,3 +1,6 @@
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
 // Symmetric-memory runtime for one NVSwitch domain (<= 8 GPUs, one process per GPU).
 //
 // Replaces the Horovod C++ core pieces that own communication memory (fusion buffer
@@ -374,6 +377,14 @@ int b200dp_fd_recv(int listen_fd, int* src, int* tag, int timeout_ms) {
   if (pr <= 0) return fail("timed out waiting for a peer fd (%d ms)", timeout_ms);
   int s = accept4(listen_fd, nullptr, nullptr, SOCK_CLOEXEC);
   if (s < 0) return fail("accept(): %s", strerror(errno));
+  {  // abstract socket names are visible to every local user: only accept handles from our own uid
+    struct ucred cred;
+    socklen_t clen = sizeof(cred);
+    if (getsockopt(s, SOL_SOCKET, SO_PEERCRED, &cred, &clen) != 0 || cred.uid != geteuid()) {
+      close(s);
+      return fail("fd_recv: rejected a connection from uid %d (expected %d)", (int)cred.uid, (int)geteuid());
+    }
+  }
   int hdr[2] = {-1, -1};
   struct iovec iov;
   iov.iov_base = hdr;

@@ -116,15 +116,32 @@ def synthetic_market_frame(n_rows: int = 20000, seed: int = 0):
 
 
 def ensure_dataset(path: str = "data_es.csv", rank: int = 0, n_rows: Optional[int] = None,
-                   allow_download: bool = True):
-    """Return the training frame: the CSV at ``path`` if present, else (rank 0 only) try the
-    download, else the synthetic frame.  Never runs at import time."""
+                   allow_download: bool = True, decide=None):
+    """Return ``(frame, source)``: the CSV at ``path`` if present, else the downloaded CSV, else the
+    synthetic frame.  Never runs at import time (the reference downloads at import on every rank,
+    app/torch_train.py:22-31).
+
+    Every rank must train on the SAME data (same length => same number of batches => matching
+    collectives), so the source is decided ONCE, by rank 0, and shared: ``decide`` is a callable
+    ``decide(value_or_None) -> value`` that broadcasts rank 0's decision (``hvd.broadcast_object`` in
+    ``app/torch_train.py``); without it (single process) the decision is local.  Rank 0 performs the
+    download; the other ranks read the file only after the decision says it exists."""
     import pandas as pd
-    if os.path.exists(path):
-        return pd.read_csv(path), "file"
-    if allow_download and os.environ.get("B200DP_OFFLINE", "0") != "1" and rank == 0:
-        if read_file_from_aws(path, timeout=float(os.environ.get("B200DP_DOWNLOAD_TIMEOUT", "3"))):
-            return pd.read_csv(path), "download"
+    source = None
+    if rank == 0:
+        if os.path.exists(path):
+            source = "file"
+        elif allow_download and os.environ.get("B200DP_OFFLINE", "0") != "1" and \
+                read_file_from_aws(path, timeout=float(os.environ.get("B200DP_DOWNLOAD_TIMEOUT", "3"))):
+            source = "download"
+        else:
+            source = "synthetic"
+    if decide is not None:
+        source = decide(source)          # blocks until rank 0 has finished (download included)
+    elif source is None:                 # rank > 0 without a broadcast: fall back to what is on disk
+        source = "file" if os.path.exists(path) else "synthetic"
+    if source in ("file", "download"):
+        return pd.read_csv(path), source
     rows = n_rows or int(os.environ.get("B200DP_SYNTH_ROWS", "20000"))
     return synthetic_market_frame(rows), "synthetic"
 

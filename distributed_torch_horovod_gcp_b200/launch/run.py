@@ -16,7 +16,18 @@ process per slot with the rank environment (both ``RANK/WORLD_SIZE/LOCAL_RANK/â€
 if any worker exits non-zero, terminate all the others (failure detection â€” SURVEY.md
 Â§5.3).  Remote hosts are reached over ``ssh`` like ``horovodrun``.  Horovod tuning flags
 are accepted and forwarded as the same ``HOROVOD_*`` environment variables the runtime
-reads (``--fusion-threshold-mb`` â†’ bucket size, ``--timeline-filename`` â†’ timeline, â€¦).
+reads (``--fusion-threshold-mb`` â†’ bucket size, ``--timeline-filename`` â†’ timeline,
+``--stall-check-*`` â†’ the device watchdog deadline, ``--log-level`` â†’ the package logger,
+``--autotune`` â†’ a start-up allreduce sweep that fills the algorithm table; flags that configure
+Horovod machinery which does not exist here â€” the polling thread, the response cache, the
+two-level allreduce â€” are reported as ignored on stderr instead of being silently swallowed).
+
+Elastic mode (``--host-discovery-script`` with ``--min-np`` / ``--max-np``; Horovod's elastic
+launcher, restart-based): the script prints ``host:slots`` lines; the job runs on
+``min(max_np, available slots)`` processes; when a worker fails, or when the workers notice through
+``state.check_host_updates()`` that the discovered host set changed (they persist the committed
+state and exit with code 75), the launcher re-runs discovery and relaunches the whole job, which
+resumes from the persisted commit (``hvd.elastic.run``).
 """
 from __future__ import annotations
 
@@ -152,9 +163,14 @@ def make_parser() -> argparse.ArgumentParser:
     p.add_argument("--stall-check-warning-time-seconds", type=int)
     p.add_argument("--stall-check-shutdown-time-seconds", type=int)
     p.add_argument("--log-level", choices=["TRACE", "DEBUG", "INFO", "WARNING", "ERROR", "FATAL"])
-    p.add_argument("--min-np", type=int)
-    p.add_argument("--max-np", type=int)
-    p.add_argument("--host-discovery-script")
+    p.add_argument("--min-np", type=int, help="elastic: fewest processes the job may run on")
+    p.add_argument("--max-np", type=int, help="elastic: most processes the job may run on")
+    p.add_argument("--host-discovery-script",
+                   help="elastic: executable printing one 'host:slots' line per available host")
+    p.add_argument("--reset-limit", type=int, default=None,
+                   help="elastic: maximum number of relaunches (default 10)")
+    p.add_argument("--elastic-timeout", type=int, default=None,
+                   help="elastic: seconds to wait for at least --min-np slots (default 600)")
     p.add_argument("command", nargs=argparse.REMAINDER)
     return p
 
@@ -176,24 +192,21 @@ def _env_for(slot: Slot, master_addr: str, master_port: int, args) -> Dict[str, 
     }
     if args.fusion_threshold_mb is not None:
         e["HOROVOD_FUSION_THRESHOLD"] = str(int(args.fusion_threshold_mb * 1024 * 1024))
-    if args.cycle_time_ms is not None:
-        e["HOROVOD_CYCLE_TIME"] = str(args.cycle_time_ms)
-    if args.cache_capacity is not None:
-        e["HOROVOD_CACHE_CAPACITY"] = str(args.cache_capacity)
-    if args.hierarchical_allreduce:
-        e["HOROVOD_HIERARCHICAL_ALLREDUCE"] = "1"
     if args.autotune:
-        e["HOROVOD_AUTOTUNE"] = "1"
+        e["HOROVOD_AUTOTUNE"] = "1"          # runtime/tuning.py: measured algorithm table at start-up
     if args.timeline_filename:
         e["HOROVOD_TIMELINE"] = args.timeline_filename
     if args.timeline_mark_cycles:
         e["HOROVOD_TIMELINE_MARK_CYCLES"] = "1"
+    # Horovod's stall inspector == the bounded spin-wait of the sm_100a kernels (runtime/symm.py reads these)
     if args.no_stall_check:
         e["HOROVOD_STALL_CHECK_DISABLE"] = "1"
     if args.stall_check_warning_time_seconds is not None:
         e["HOROVOD_STALL_CHECK_TIME_SECONDS"] = str(args.stall_check_warning_time_seconds)
     if args.stall_check_shutdown_time_seconds is not None:
         e["HOROVOD_STALL_SHUTDOWN_TIME_SECONDS"] = str(args.stall_check_shutdown_time_seconds)
+    if getattr(args, "_elastic_env", None):
+        e.update(args._elastic_env)
     if args.log_level:
         e["HOROVOD_LOG_LEVEL"] = args.log_level
     if args.start_timeout is not None:
@@ -238,40 +251,44 @@ def check_build() -> str:
     return "\n".join(out)
 
 
-def run(argv: Optional[Sequence[str]] = None) -> int:
-    parser = make_parser()
-    args = parser.parse_args(argv)
-    if args.version:
-        from .. import __version__
-        print(__version__)
-        return 0
-    if args.check_build:
-        print(check_build())
-        return 0
-    if args.mpi:
-        parser.error("--mpi: this runtime has no MPI controller; use the default (Gloo) control plane")
-    if args.np is None:
-        parser.error("-np is required")
-    if args.np <= 0:
-        parser.error("-np must be positive")
-    cmd = list(args.command)
-    if cmd and cmd[0] == "--":
-        cmd = cmd[1:]
-    if not cmd:
-        parser.error("no command given")
-    if args.hosts and args.hostfile:
-        parser.error("only one of -H / --hostfile may be given")
-    if args.hostfile:
-        hosts = parse_hostfile(args.hostfile)
-    elif args.hosts:
-        hosts = parse_hosts(args.hosts)
-    else:
-        hosts = [("localhost", args.np)]
-    try:
-        slots = build_slots(hosts, args.np)
-    except ValueError as e:
-        parser.error(str(e))
+RESTART_EXIT = 75     # a worker asks for a relaunch (discovered hosts changed); EX_TEMPFAIL
 
+
+def discover_hosts(script: str) -> List[Tuple[str, int]]:
+    """Run the host-discovery script: one ``host:slots`` (or ``host slots=N`` / bare ``host``) per line."""
+    r = subprocess.run([script], capture_output=True, text=True, timeout=60)
+    if r.returncode != 0:
+        raise RuntimeError(f"host discovery script {script} failed ({r.returncode}): {r.stderr.strip()}")
+    hosts: List[Tuple[str, int]] = []
+    for line in r.stdout.splitlines():
+        line = line.split("#", 1)[0].strip()
+        if not line:
+            continue
+        if "slots=" in line:
+            parts = line.split()
+            hosts.append((parts[0], int(parts[1].split("=", 1)[1])))
+        else:
+            hosts.extend(parse_hosts(line))
+    return hosts
+
+
+def _warn_ignored(args):
+    ignored = []
+    if args.cycle_time_ms is not None:
+        ignored.append("--cycle-time-ms (no polling thread: buckets launch from autograd hooks)")
+    if args.cache_capacity is not None:
+        ignored.append("--cache-capacity (no response cache: the bucket plan is static)")
+    if args.hierarchical_allreduce:
+        ignored.append("--hierarchical-allreduce (one NVSwitch domain: every peer is one hop away)")
+    if args.disable_cache:
+        ignored.append("--disable-cache (no response cache)")
+    for i in ignored:
+        print(f"[launcher] ignored: {i}", file=sys.stderr)
+
+
+def launch_once(args, hosts: Sequence[Tuple[str, int]], np: int, cmd: List[str]) -> int:
+    """Spawn ``np`` workers on ``hosts``, multiplex their output, kill all on the first failure."""
+    slots = build_slots(hosts, np)
     all_local = all(s.hostname in LOCAL_NAMES or s.hostname == socket.gethostname() for s in slots)
     master_addr = "127.0.0.1" if all_local else slots[0].hostname
     master_port = args.master_port or _free_port()
@@ -307,7 +324,7 @@ def run(argv: Optional[Sequence[str]] = None) -> int:
         if args.output_filename:
             d = os.path.join(args.output_filename, f"rank.{slot.rank}")
             os.makedirs(d, exist_ok=True)
-            out_f, err_f = open(os.path.join(d, "stdout"), "w"), open(os.path.join(d, "stderr"), "w")
+            out_f, err_f = open(os.path.join(d, "stdout"), "a"), open(os.path.join(d, "stderr"), "a")
             logs += [out_f, err_f]
         pre_o = f"[{slot.rank}]<stdout>:" if len(slots) > 1 else ""
         pre_e = f"[{slot.rank}]<stderr>:" if len(slots) > 1 else ""
@@ -362,6 +379,89 @@ def run(argv: Optional[Sequence[str]] = None) -> int:
         for f in logs:
             f.close()
     return exit_code
+
+
+def run(argv: Optional[Sequence[str]] = None) -> int:
+    parser = make_parser()
+    args = parser.parse_args(argv)
+    if args.version:
+        from .. import __version__
+        print(__version__)
+        return 0
+    if args.check_build:
+        print(check_build())
+        return 0
+    if args.mpi:
+        parser.error("--mpi: this runtime has no MPI controller; use the default (Gloo) control plane")
+    elastic = args.host_discovery_script is not None
+    if (args.min_np is not None or args.max_np is not None) and not elastic:
+        parser.error("--min-np / --max-np need --host-discovery-script (elastic mode)")
+    if args.np is None and not elastic:
+        parser.error("-np is required")
+    if args.np is not None and args.np <= 0:
+        parser.error("-np must be positive")
+    cmd = list(args.command)
+    if cmd and cmd[0] == "--":
+        cmd = cmd[1:]
+    if not cmd:
+        parser.error("no command given")
+    if args.hosts and args.hostfile:
+        parser.error("only one of -H / --hostfile may be given")
+    _warn_ignored(args)
+
+    if not elastic:
+        if args.hostfile:
+            hosts = parse_hostfile(args.hostfile)
+        elif args.hosts:
+            hosts = parse_hosts(args.hosts)
+        else:
+            hosts = [("localhost", args.np)]
+        try:
+            build_slots(hosts, args.np)
+        except ValueError as e:
+            parser.error(str(e))
+        return launch_once(args, hosts, args.np, cmd)
+
+    # ------------------------------------------------------------------ elastic (restart-based)
+    script = os.path.abspath(args.host_discovery_script)
+    if not os.access(script, os.X_OK):
+        parser.error(f"--host-discovery-script {script} is not executable")
+    min_np = args.min_np or args.np or 1
+    max_np = args.max_np or args.np or (1 << 30)
+    if min_np > max_np:
+        parser.error("--min-np must not exceed --max-np")
+    reset_limit = args.reset_limit if args.reset_limit is not None else 10
+    wait_s = args.elastic_timeout if args.elastic_timeout is not None else 600
+    state_dir = os.environ.get("B200DP_ELASTIC_STATE_DIR") or os.path.join(
+        os.getcwd(), f".b200dp_elastic_{os.getpid()}")
+    os.makedirs(state_dir, exist_ok=True)
+    resets = 0
+    while True:
+        deadline = time.time() + wait_s
+        while True:
+            hosts = discover_hosts(script)
+            total = sum(s for _, s in hosts)
+            if total >= min_np:
+                break
+            if time.time() > deadline:
+                print(f"[launcher] elastic: only {total} slot(s) discovered, need --min-np {min_np}; giving up",
+                      file=sys.stderr)
+                return 1
+            time.sleep(1.0)
+        np = min(max_np, total)
+        spec = ",".join(f"{h}:{s}" for h, s in hosts)
+        args._elastic_env = {"HOROVOD_ELASTIC": "1", "B200DP_DISCOVERY_SCRIPT": script,
+                             "B200DP_ELASTIC_HOSTS": spec, "B200DP_ELASTIC_STATE_DIR": state_dir,
+                             "B200DP_ELASTIC_RESET": str(resets)}
+        print(f"[launcher] elastic: launching {np} process(es) on {spec} (reset {resets})", file=sys.stderr)
+        rc = launch_once(args, hosts, np, cmd)
+        if rc == 0:
+            return 0
+        if rc == 130 or resets >= reset_limit:
+            return rc
+        resets += 1
+        why = "hosts changed" if rc == RESTART_EXIT else f"a worker failed (exit {rc})"
+        print(f"[launcher] elastic: {why}; re-running host discovery", file=sys.stderr)
 
 
 def main():

@@ -349,5 +349,35 @@ class FusedEngine:
             self.step_ctr.fill_(steps)
         self.params_changed()
 
+    def release(self):
+        """Detach the model from the symmetric arenas (parameters and gradients become ordinary
+        device tensors holding the current values) and drop every arena view, so the runtime can unmap
+        and release the memory (``hvd.shutdown()``)."""
+        if getattr(self, "_released", False) or not hasattr(self.symm, "free"):
+            return
+        self._released = True
+        try:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+            torch.cuda.synchronize(self.device)
+        except Exception:      # noqa: BLE001
+            pass
+        with torch.no_grad():
+            for b in self.buckets:
+                for s in b.slots:
+                    p = s.param
+                    p.data = p.data.clone(memory_format=torch.preserve_format)
+                    if p.grad is not None:
+                        p.grad = p.grad.clone(memory_format=torch.preserve_format)
+        for ar in self.arenas.values():
+            for key in ("G", "P"):
+                buf = ar.get(key)
+                if buf is not None and hasattr(self.symm, "free"):
+                    try:
+                        self.symm.free(buf)
+                    except Exception:  # noqa: BLE001
+                        pass
+            ar["g"] = ar["p"] = ar["G"] = ar["P"] = None
+        self._args.clear()
+
     def algorithms(self) -> Dict[int, str]:
         return {i: self.S.ALGO_NAMES[a] for i, a in self._algo.items()}

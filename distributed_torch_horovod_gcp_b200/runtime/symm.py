@@ -23,7 +23,7 @@ import torch.distributed as dist
 from . import lib as _lib
 
 MAX_RANKS, MAX_BLOCKS, NUM_CHANNELS = 8, 128, 4
-CH_ENGINE, CH_USER, CH_BCAST = 0, 1, 2
+CH_ENGINE, CH_USER, CH_BCAST, CH_OPT = 0, 1, 2, 3
 ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS = 0, 1, 2
 ALGO_NAMES = {0: "oneshot", 1: "twoshot", 2: "nvls"}
 _DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
@@ -60,6 +60,16 @@ class BcastArgs(ctypes.Structure):
                 ("use_mc", ctypes.c_int), ("pad_", ctypes.c_int)]
 
 
+class CollArgs(ctypes.Structure):
+    _fields_ = [("src", ctypes.c_uint64 * MAX_RANKS), ("dst", ctypes.c_uint64 * MAX_RANKS),
+                ("src_mc", ctypes.c_uint64), ("dst_mc", ctypes.c_uint64), ("chunk", ctypes.c_uint64),
+                ("scale", ctypes.c_float), ("channel", ctypes.c_int), ("use_mc", ctypes.c_int),
+                ("pad_", ctypes.c_int)]
+
+
+COLL_REDUCE_SCATTER, COLL_ALLGATHER, COLL_ALLTOALL = 0, 1, 2
+
+
 class _Raw:
     """Expose a raw device range through ``__cuda_array_interface__`` (zero-copy into torch)."""
 
@@ -88,6 +98,26 @@ class SymmBuffer:
 
     def ptrs_at(self, byte_offset: int) -> List[int]:
         return [p + byte_offset for p in self.peer_ptrs]
+
+
+def watchdog_seconds() -> float:
+    """Deadline of the in-kernel bounded spin-wait (Horovod's stall inspector, on the device).
+    ``B200DP_KERNEL_TIMEOUT_S`` wins; otherwise Horovod's knobs are honoured:
+    ``HOROVOD_STALL_SHUTDOWN_TIME_SECONDS`` (``--stall-check-shutdown-time-seconds``), else
+    ``HOROVOD_STALL_CHECK_TIME_SECONDS`` (``--stall-check-warning-time-seconds``: there is no separate
+    warning phase on the device, the deadline is the warning time); ``HOROVOD_STALL_CHECK_DISABLE=1``
+    (``--no-stall-check``) disables it (one week).  Default 300 s — NCCL-like minutes, so that a rank
+    that is merely slow (checkpointing, data stall) does not abort a healthy job."""
+    v = os.environ.get("B200DP_KERNEL_TIMEOUT_S")
+    if v:
+        return float(v)
+    if os.environ.get("HOROVOD_STALL_CHECK_DISABLE", "0") == "1":
+        return 7 * 24 * 3600.0
+    for k in ("HOROVOD_STALL_SHUTDOWN_TIME_SECONDS", "HOROVOD_STALL_CHECK_TIME_SECONDS"):
+        v = os.environ.get(k)
+        if v and float(v) > 0:
+            return float(v)
+    return 300.0
 
 
 class SymmRuntime:
@@ -158,7 +188,7 @@ class SymmRuntime:
             self.ctx.sig[r] = self.sig.peer_ptrs[r]
         self.ctx.epoch = self.epoch.data_ptr()
         self.ctx.err = dp.value
-        self.ctx.timeout_ns = int(float(os.environ.get("B200DP_KERNEL_TIMEOUT_S", "20")) * 1e9)
+        self.ctx.timeout_ns = int(watchdog_seconds() * 1e9)
         self.ctx.rank, self.ctx.world = self.rank, self.world
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)
@@ -197,6 +227,10 @@ class SymmRuntime:
         L.b200dp_can_access_peer.argtypes = [i, i]
         L.b200dp_comm_allreduce.argtypes = [P(CommCtx), P(ARArgs), i, i, i, i, u64]
         L.b200dp_comm_broadcast.argtypes = [P(CommCtx), P(BcastArgs), i, i, u64]
+        if hasattr(L, "b200dp_comm_collective"):
+            L.b200dp_comm_collective.argtypes = [P(CommCtx), P(CollArgs), i, i, i, i, u64]
+            if L.b200dp_comm_coll_bytes() != ctypes.sizeof(CollArgs):
+                raise RuntimeError("ctypes/C struct layout mismatch: CollArgs")
         lim = [ctypes.c_int() for _ in range(6)]
         L.b200dp_comm_limits(*[ctypes.byref(x) for x in lim])
         got = tuple(x.value for x in lim)
@@ -349,11 +383,23 @@ class SymmRuntime:
             raise RuntimeError((self.lib.b200dp_comm_last_error() or b"").decode())
         self.launches += 1
 
+    def _lane(self, lane: int):
+        """(staging buffer, signal channel) of a lane.  Lane 0 serves user collectives on the caller's
+        stream; lane 1 is private to DistributedOptimizer's un-fused bucket path, which runs on its own
+        side stream concurrently with user collectives — sharing one staging buffer and one set of
+        barrier counters between two streams would corrupt both."""
+        if lane == 0:
+            return self.stage, CH_USER
+        if getattr(self, "stage_opt", None) is None:
+            self.stage_opt = self.alloc(self.stage_bytes)      # collective: every rank takes this path together
+        return self.stage_opt, CH_OPT
+
     def allreduce_(self, t: torch.Tensor, prescale: float = 1.0, postscale: float = 1.0,
-                   algo: Optional[int] = None) -> torch.cuda.Event:
+                   algo: Optional[int] = None, lane: int = 0) -> torch.cuda.Event:
         """In-place sum-allreduce of ``t`` (scaled by prescale*postscale) on the current
         stream.  Zero-copy when ``t`` lives in symmetric memory; staged otherwise."""
         stream = torch.cuda.current_stream(self.device)
+        stage, channel = self._lane(lane)
         scale = float(prescale) * float(postscale)
         es = t.element_size()
         work = t if t.is_contiguous() else t.contiguous()
@@ -361,18 +407,18 @@ class SymmRuntime:
         vec = 16 // es
         if loc is not None and loc[1] % 16 == 0 and (work.numel() % vec == 0):
             buf, off = loc
-            self._ar_symm(buf, off, work.numel(), work.dtype, scale, stream, algo)
+            self._ar_symm(buf, off, work.numel(), work.dtype, scale, stream, algo, channel=channel)
         else:
             flat = work.view(-1)
             cap = (self.stage_bytes // es) // (vec * self.world) * (vec * self.world)
-            st = self.stage.tensor(work.dtype)
+            st = stage.tensor(work.dtype)
             for lo in range(0, flat.numel(), cap):
                 m = min(cap, flat.numel() - lo)
                 mp = (m + vec - 1) // vec * vec
                 st[:m].copy_(flat[lo:lo + m])
                 if mp != m:
                     st[m:mp].zero_()
-                self._ar_symm(self.stage, 0, mp, work.dtype, scale, stream, algo, user=True)
+                self._ar_symm(stage, 0, mp, work.dtype, scale, stream, algo, user=True, channel=channel)
                 flat[lo:lo + m].copy_(st[:m])
         if work is not t:
             t.copy_(work)
@@ -421,7 +467,7 @@ class SymmRuntime:
         return launch
 
     def _ar_symm(self, buf: SymmBuffer, off: int, numel: int, dtype, scale, stream, algo,
-                 user: bool = False):
+                 user: bool = False, channel: int = CH_USER):
         es = torch.empty((), dtype=dtype).element_size()
         nbytes = numel * es
         a = ARArgs()
@@ -429,7 +475,7 @@ class SymmRuntime:
         for r in range(self.world):
             a.inp[r] = ptrs[r]
             a.out[r] = ptrs[r]
-        a.n, a.scale, a.channel = numel, scale, CH_USER
+        a.n, a.scale, a.channel = numel, scale, channel
         a.h.kind = OPT_NONE
         algo = self.pick_algo(nbytes, need_mc=buf.mc_ptr != 0) if algo is None else algo
         if algo == ALGO_NVLS and buf.mc_ptr == 0:
@@ -438,11 +484,90 @@ class SymmRuntime:
             a.in_mc = buf.mc_ptr + off
             a.out_mc = buf.mc_ptr + off
         if algo == ALGO_ONESHOT:
-            if nbytes > self.scratch.numel():
-                self.scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            a.scratch = self.scratch.data_ptr()
+            key = "scratch" if channel == CH_USER else "scratch_opt"
+            sc = getattr(self, key, None)
+            if sc is None or nbytes > sc.numel():
+                sc = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=self.device)
+                setattr(self, key, sc)
+            a.scratch = sc.data_ptr()
             a.copy_back = 1
         self.launch_allreduce(a, algo, dtype, nbytes, stream)
+
+    # ------------------------------------------------------------------ reduce-scatter / all-gather / all-to-all
+    def _coll(self, mode: int, a: CollArgs, dtype, work_bytes: int, stream):
+        blocks = max(1, min((work_bytes + 512 * 16 * 2 - 1) // (512 * 16 * 2), self.max_blocks or 48))
+        rc = self.lib.b200dp_comm_collective(ctypes.byref(self.ctx), ctypes.byref(a), mode,
+                                             _DTYPE_CODE.get(dtype, 0), blocks, 512, stream.cuda_stream)
+        if rc != 0:
+            raise RuntimeError((self.lib.b200dp_comm_last_error() or b"").decode())
+        self.launches += 1
+
+    def reducescatter(self, src: torch.Tensor, out: torch.Tensor, scale: float = 1.0) -> torch.cuda.Event:
+        """``out`` (numel = src.numel() / world) = scale * sum over ranks of chunk ``rank`` of ``src``.
+        ``src`` is staged into symmetric memory (chunk-major slabs when larger than the staging
+        buffer); each rank then reads ONLY its own chunk from every peer (or lets the switch sum it)."""
+        stream = torch.cuda.current_stream(self.device)
+        W, es = self.world, src.element_size()
+        vec = 16 // es
+        chunk = src.numel() // W
+        assert src.numel() == chunk * W and out.numel() == chunk and chunk % vec == 0
+        s2, o1 = src.reshape(W, chunk), out.reshape(chunk)
+        cap = (self.stage_bytes // es) // (W * vec) * vec            # elements per rank chunk per slab
+        st = self.stage.tensor(src.dtype)
+        for lo in range(0, chunk, cap):
+            m = min(cap, chunk - lo)
+            st[: W * m].view(W, m).copy_(s2[:, lo:lo + m])
+            a = CollArgs()
+            for r in range(W):
+                a.src[r] = self.stage.peer_ptrs[r]
+            dst = o1[lo:lo + m]
+            a.dst[self.rank] = dst.data_ptr()
+            a.chunk, a.scale, a.channel = m, float(scale), CH_USER
+            a.use_mc = 1 if (self.stage.mc_ptr and m * es >= (64 << 10)) else 0
+            a.src_mc = self.stage.mc_ptr
+            self._coll(COLL_REDUCE_SCATTER, a, src.dtype, m * es, stream)
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        return ev
+
+    def allgather(self, src: torch.Tensor, out: torch.Tensor) -> torch.cuda.Event:
+        """``out`` (world * src.numel()) = concatenation of every rank's ``src`` (equal sizes, 16-byte
+        multiple).  Each rank pushes its chunk into slot ``rank`` of every peer's staging buffer."""
+        return self._push(COLL_ALLGATHER, src, out)
+
+    def alltoall(self, src: torch.Tensor, out: torch.Tensor) -> torch.cuda.Event:
+        """Equal-split all-to-all: chunk j of ``src`` lands in slot ``rank`` of rank j's ``out``."""
+        return self._push(COLL_ALLTOALL, src, out)
+
+    def _push(self, mode: int, src: torch.Tensor, out: torch.Tensor) -> torch.cuda.Event:
+        stream = torch.cuda.current_stream(self.device)
+        W = self.world
+        sb = src.reshape(-1).view(torch.uint8)
+        ob = out.reshape(-1).view(torch.uint8)
+        chunk = sb.numel() if mode == COLL_ALLGATHER else sb.numel() // W     # bytes per (src, dst) pair
+        assert chunk % 16 == 0 and ob.numel() == chunk * W
+        cap = (self.stage_bytes // W) // 16 * 16
+        st = self.stage.tensor(torch.uint8)
+        o2 = ob.view(W, chunk)
+        for lo in range(0, chunk, cap):
+            m = min(cap, chunk - lo)
+            a = CollArgs()
+            if mode == COLL_ALLGATHER:
+                piece = sb[lo:lo + m]
+            else:                                   # pack the W sub-chunks of this slab contiguously
+                piece = sb.view(W, chunk)[:, lo:lo + m].contiguous().view(-1)
+            a.src[self.rank] = piece.data_ptr()
+            for r in range(W):
+                a.dst[r] = self.stage.peer_ptrs[r]
+            a.chunk, a.channel = m // 16, CH_USER
+            a.use_mc = 1 if (mode == COLL_ALLGATHER and self.stage.mc_ptr and m >= (64 << 10)) else 0
+            a.dst_mc = self.stage.mc_ptr
+            self._coll(mode, a, torch.uint8, m, stream)
+            o2[:, lo:lo + m].copy_(st[: W * m].view(W, m))
+            piece.record_stream(stream) if piece.data_ptr() != sb.data_ptr() else None
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        return ev
 
     def broadcast_(self, t: torch.Tensor, root: int) -> torch.cuda.Event:
         stream = torch.cuda.current_stream(self.device)
@@ -494,13 +619,59 @@ class SymmRuntime:
                 f"(block {block}, channel {ch}) — a peer died, hung or ran a different "
                 f"collective sequence")
 
+    def reset_errors(self):
+        """Collective: clear the watchdog mailbox and restart the cross-rank barrier protocol from zero
+        (signal pads + epoch counters), so a retry after a failed collective (``hvd.elastic.run``) does
+        not trip over the stale state of the run that timed out."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        for i in range(4):
+            self._mailbox[i] = 0
+        self.sig.tensor(torch.int32).zero_()
+        self.epoch.zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
     def close(self):
+        """Release everything this runtime mapped: multicast bindings, peer mappings and the cuMem
+        handles of every symmetric allocation (``hvd.shutdown(); hvd.init()`` cycles — what
+        ``hvd.elastic.run`` does after a failure — must not leak 64 MiB of staging plus all arenas).
+        Tensors that still alias a released range must not be used afterwards; the fused engine drops
+        its arena views in ``FusedEngine.release()``, which ``hvd.shutdown()`` calls first."""
         try:
             torch.cuda.synchronize(self.device)
         except Exception:
             pass
+        for buf in list(getattr(self, "buffers", [])):
+            try:
+                self.free(buf)
+            except Exception:      # noqa: BLE001 - best effort at teardown
+                pass
+        self.buffers = []
+        self.stage = self.stage_opt = None
         if getattr(self, "_sock", -1) >= 0:
             self.lib.b200dp_fd_close(self._sock)
             self._sock = -1
-        # mappings are reclaimed at process exit; explicit unmap is skipped on purpose because
-        # torch tensors may still alias the ranges.
+
+    def free(self, buf: SymmBuffer):
+        """Unmap and release one symmetric allocation (local mapping, every peer mapping, the multicast
+        mapping and binding).  Local operation; call it on every rank."""
+        if buf._handles is None:
+            return
+        buf._bytes = None
+        mc = buf._handles.get("mc", 0)
+        if buf.mc_ptr:
+            self.lib.b200dp_mem_unmap(buf.mc_ptr, buf.padded)
+            if mc:
+                self.lib.b200dp_mc_unbind(mc, self.dev_index, 0, buf.padded)
+        if mc:
+            self.lib.b200dp_mem_release(mc)
+        for r, va in enumerate(buf.peer_ptrs):
+            self.lib.b200dp_mem_unmap(va, buf.padded)
+        for r, h in buf._handles.get("mem", {}).items():
+            self.lib.b200dp_mem_release(h)
+        buf._handles = None
+        buf.mc_ptr = 0
+        buf.peer_ptrs = []
+        if buf in self.buffers:
+            self.buffers.remove(buf)

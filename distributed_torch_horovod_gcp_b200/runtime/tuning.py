@@ -73,3 +73,42 @@ def derive_from_sweep(rows, world: int, multicast: bool) -> dict:
     if multicast and "nvls_us" in last and last["nvls_us"] <= last.get("twoshot_us", float("inf")):
         prefer = "nvls"
     return {"oneshot_max_bytes": int(oneshot_max), "prefer": prefer}
+
+
+def autotune(symm, sizes=(4 << 10, 16 << 10, 64 << 10, 256 << 10, 1 << 20, 4 << 20, 16 << 20),
+             iters: int = 8) -> dict:
+    """``horovodrun --autotune`` / ``HOROVOD_AUTOTUNE=1``: measure the three allreduce kernels on THIS
+    machine at start-up (collective; ~0.2 s) and install the derived row for this world size — the
+    measured replacement for Horovod's Bayesian parameter_manager.  Times are CUDA-event device times,
+    max over ranks."""
+    import torch
+    import torch.distributed as dist
+    global _loaded
+    world = symm.world
+    buf = symm.alloc_tensor(max(sizes) // 4, torch.float32)
+    buf.zero_()
+    rows = []
+    algos = [("oneshot", ONESHOT), ("twoshot", TWOSHOT)] + ([("nvls", NVLS)] if symm.multicast else [])
+    for nbytes in sizes:
+        t = buf[: nbytes // 4]
+        row = {"bytes": nbytes}
+        for name, code in algos:
+            launch = symm.prepare_allreduce(t, scale=1.0, algo=code)
+            for _ in range(2):
+                launch()
+            torch.cuda.synchronize(symm.device)
+            dist.barrier(group=symm.group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                launch()
+            e1.record()
+            torch.cuda.synchronize(symm.device)
+            us = torch.tensor([e0.elapsed_time(e1) * 1e3 / iters], dtype=torch.float64)
+            dist.all_reduce(us, op=dist.ReduceOp.MAX, group=symm.group)
+            row[name + "_us"] = float(us)
+        rows.append(row)
+    derived = derive_from_sweep(rows, world, bool(symm.multicast))
+    table()[str(world)] = derived
+    symm.check_errors()
+    return {"rows": rows, "table": derived}

@@ -30,8 +30,7 @@ from .process_sets import ProcessSet, global_process_set, add_process_set, remov
 from . import elastic
 
 
-class HostsUpdatedInterrupt(RuntimeError):
-    """Raised in elastic mode when the host set changed (API parity; see ``elastic``)."""
+HostsUpdatedInterrupt = elastic.HostsUpdatedInterrupt   # raised by state.check_host_updates()
 
 
 # ---------------------------------------------------------------- build / capability probes

@@ -4,8 +4,13 @@ a collective fails (``HorovodInternalError``).
 
 The reference enables none of this; it is provided for surface parity and
 as the failure-recovery hook for the kernel watchdog (a bounded spin-wait in the sm_100a
-kernels sets an error flag -> ``HorovodInternalError``).  Dynamic host discovery /
-re-rendezvous with a different world size is out of scope.
+kernels sets an error flag -> ``HorovodInternalError``).
+
+Resizing is restart-based (launch/run.py elastic mode): ``state.check_host_updates()`` lets rank 0
+re-run the launcher's host-discovery script; when the host set differs from the one the job was
+launched on every rank raises ``HostsUpdatedInterrupt``, ``run`` persists the last commit
+(``B200DP_ELASTIC_STATE_DIR``) and the workers exit with code 75, which makes the launcher relaunch
+on the new host set; the new workers start from the persisted commit.
 """
 from __future__ import annotations
 
@@ -15,6 +20,16 @@ import functools
 import torch
 
 from .mpi_ops import HorovodInternalError
+
+RESTART_EXIT = 75
+
+
+class HostsUpdatedInterrupt(RuntimeError):
+    """The set of available hosts changed (Horovod's exception of the same name)."""
+
+    def __init__(self, skip_sync: bool = False):
+        super().__init__("hosts updated")
+        self.skip_sync = skip_sync
 
 
 class State:
@@ -44,7 +59,65 @@ class State:
         self.save()
 
     def check_host_updates(self):
+        """Raise ``HostsUpdatedInterrupt`` on every rank when the launcher's discovery script reports a
+        host set different from the one this job runs on.  No-op outside elastic launches; rank 0 runs
+        the script at most every ``B200DP_DISCOVERY_INTERVAL_S`` seconds (default 5)."""
+        import os
+        import subprocess
+        import time
+        script = os.environ.get("B200DP_DISCOVERY_SCRIPT")
+        if not script:
+            return None
+        from .. import _state
+        from .functions import broadcast_object
+        changed = False
+        if _state.rank() == 0:
+            now = time.time()
+            every = float(os.environ.get("B200DP_DISCOVERY_INTERVAL_S", "5"))
+            if now - getattr(self, "_last_discovery", 0.0) >= every:
+                self._last_discovery = now
+                try:
+                    from ..launch.run import discover_hosts
+                    spec = ",".join(f"{h}:{s}" for h, s in discover_hosts(script))
+                    changed = spec != os.environ.get("B200DP_ELASTIC_HOSTS", spec)
+                except (RuntimeError, subprocess.SubprocessError, OSError):
+                    changed = False
+        changed = broadcast_object(changed, 0)
+        if changed:
+            raise HostsUpdatedInterrupt()
         return None
+
+    # -- persistence across an elastic relaunch ------------------------------------------
+    def _persist_path(self):
+        import os
+        d = os.environ.get("B200DP_ELASTIC_STATE_DIR")
+        return os.path.join(d, "state.pt") if d else None
+
+    def persist(self):
+        """Rank 0 writes the last commit to disk (atomic rename)."""
+        import os
+        from .. import _state
+        path = self._persist_path()
+        if path is None or _state.rank() != 0:
+            return
+        tmp = path + ".tmp"
+        torch.save(self._persist_payload(), tmp)
+        os.replace(tmp, path)
+
+    def load_persisted(self) -> bool:
+        import os
+        path = self._persist_path()
+        if path is None or not os.path.exists(path):
+            return False
+        self._load_payload(torch.load(path, map_location="cpu", weights_only=False))
+        return True
+
+    def _persist_payload(self):
+        return {"attrs": dict(self._saved)}
+
+    def _load_payload(self, payload):
+        self._saved = dict(payload["attrs"])
+        self.restore()
 
     def sync(self):
         from .functions import broadcast_object
@@ -82,6 +155,17 @@ class TorchState(State):
             if eng is not None:
                 eng.params_changed()
                 eng.import_state()
+
+    def _persist_payload(self):
+        return {"attrs": dict(self._saved), "model": self._model_sd, "opt": self._opt_sd}
+
+    def _load_payload(self, payload):
+        dev = next(self.model.parameters()).device if self.model is not None else None
+        if payload.get("model") is not None and dev is not None:
+            self._model_sd = {k: v.to(dev) for k, v in payload["model"].items()}
+        self._opt_sd = payload.get("opt")
+        self._saved = dict(payload["attrs"])
+        self.restore()
 
     def sync(self):
         from .functions import broadcast_parameters, broadcast_optimizer_state
@@ -152,15 +236,33 @@ def run(func):
 
     @functools.wraps(func)
     def wrapper(state, *args, **kwargs):
+        import sys
         retries = int(os.environ.get("B200DP_ELASTIC_MAX_RETRIES", "3"))
+        from .. import _state
+        if _state.rank() == 0:
+            state.load_persisted()          # resuming after an elastic relaunch
         state.sync()
         while True:
             try:
                 return func(state, *args, **kwargs)
+            except HostsUpdatedInterrupt:
+                # the world is about to change: keep the last commit, hand control back to the launcher
+                state.persist()
+                from . import mpi_ops
+                try:
+                    mpi_ops.barrier()
+                except Exception:      # noqa: BLE001
+                    pass
+                sys.stdout.flush()
+                sys.stderr.flush()
+                os._exit(RESTART_EXIT)
             except HorovodInternalError:
                 if retries <= 0:
                     raise
                 retries -= 1
+                symm = _state.runtime().symm
+                if symm is not None:
+                    symm.reset_errors()     # clear the watchdog mailbox and the barrier counters (collective)
                 state.restore()
                 state.on_reset()
                 state.sync()

@@ -7,7 +7,9 @@ N8, N10; used by the reference through app/torch_train.py:259,266).
 Data plane selection per tensor:
   * CPU tensor            -> Gloo (``torch.distributed``), the CPU plumbing configuration.
   * CUDA tensor           -> symmetric-memory sm_100a kernels (one-shot / two-shot / NVLS
-                             allreduce, multicast broadcast) from ``runtime.symm``.
+                             allreduce, multicast broadcast, reduce-scatter, all-gather,
+                             equal-split all-to-all) from ``runtime.symm``; ragged all-gather /
+                             all-to-all shapes keep the torch.distributed path.
   * CUDA tensor, no symm  -> NCCL fallback (warned once at runtime creation).
 
 Handles are small integers, as in Horovod.  For CUDA work a handle wraps a CUDA event;
@@ -119,6 +121,9 @@ def _finish(h: _Handle):
                                       else None).wait_event(h.event)
             if os.environ.get("HOROVOD_SYNC_HOST", "0") == "1":
                 h.event.synchronize()
+            symm = _state.runtime().symm
+            if symm is not None:
+                symm.check_errors()     # a bounded spin-wait expired in an earlier kernel (host-mapped mailbox)
     except RuntimeError as e:  # surfaced collective failure
         raise HorovodInternalError(str(e)) from e
     if h.post is not None:
@@ -180,7 +185,8 @@ def _timeline(name: str, phase: str, **kw):
 
 # ----------------------------------------------------------------------------- allreduce
 def _allreduce_impl(tensor: torch.Tensor, output: torch.Tensor, op, prescale: float,
-                    postscale: float, name: Optional[str], process_set, async_: bool) -> _Handle:
+                    postscale: float, name: Optional[str], process_set, async_: bool,
+                    lane: int = 0) -> _Handle:
     _check_op(op)
     rt = _rt()
     n = _ps_size(process_set)
@@ -196,7 +202,7 @@ def _allreduce_impl(tensor: torch.Tensor, output: torch.Tensor, op, prescale: fl
     if output.is_cuda and process_set is None:
         symm = _state.get_symm()
         if symm is not None and op.value in (0, 1) and symm.supports(output.dtype):
-            ev = symm.allreduce_(output, prescale=prescale, postscale=postscale)
+            ev = symm.allreduce_(output, prescale=prescale, postscale=postscale, lane=lane)
             return _Handle(output, event=ev, name=name)
     if prescale != 1.0:
         output.mul_(prescale)
@@ -220,10 +226,12 @@ def allreduce_async(tensor, average=None, name=None, op=None, prescale_factor=1.
 
 
 def allreduce_async_(tensor, average=None, name=None, op=None, prescale_factor=1.0,
-                     postscale_factor=1.0, process_set=None) -> int:
+                     postscale_factor=1.0, process_set=None, _lane: int = 0) -> int:
+    """``_lane`` (internal): 1 = DistributedOptimizer's side-stream bucket path, which gets its own
+    staging buffer and barrier channel so it can overlap user collectives on the main stream."""
     op = _resolve_op(average, op)
     return _handles.add(_allreduce_impl(tensor, tensor, op, prescale_factor, postscale_factor,
-                                        name, process_set, True))
+                                        name, process_set, True, lane=_lane))
 
 
 def _resolve_op(average, op):
@@ -385,6 +393,14 @@ def allgather_async(tensor, name=None, process_set=None) -> int:
                            (process_set.group if process_set is not None and process_set.group
                             else rt.cpu_group))
     mx = max(sizes)
+    symm = _state.get_symm() if (tensor.is_cuda and process_set is None) else None
+    row_bytes = (tensor.numel() // max(tensor.shape[0], 1)) * tensor.element_size() if tensor.shape[0] else 0
+    if symm is not None and min(sizes) == mx and mx > 0 and (mx * row_bytes) % 16 == 0:
+        # equal shards: every rank pushes its shard into slot `rank` of all peers over NVLink (sm_100a kernel)
+        src = tensor.contiguous()
+        out = torch.empty((n * mx,) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+        ev = symm.allgather(src, out)
+        return _handles.add(_Handle(out, event=ev, name=name))
     pad = tensor
     if tensor.shape[0] != mx:
         pad = torch.zeros((mx,) + tuple(tensor.shape[1:]), dtype=tensor.dtype,
@@ -423,6 +439,14 @@ def alltoall_async(tensor, splits=None, name=None, process_set=None) -> int:
         send = [int(s) for s in (splits.tolist() if isinstance(splits, torch.Tensor) else splits)]
         if len(send) != n or sum(send) != tensor.shape[0]:
             raise ValueError("splits must have one entry per rank and sum to tensor.shape[0]")
+    if splits is None and tensor.is_cuda and process_set is None:
+        symm = _state.get_symm()
+        per = tensor.numel() // n * tensor.element_size()
+        if symm is not None and per > 0 and per % 16 == 0:
+            src = tensor.contiguous()
+            out = torch.empty_like(src)
+            ev = symm.alltoall(src, out)
+            return _handles.add(_Handle(out, event=ev, name=name))
     ctl = process_set.group if process_set is not None and process_set.group else rt.cpu_group
     all_send = [None] * n
     dist.all_gather_object(all_send, send, group=ctl)
@@ -479,6 +503,17 @@ def reducescatter_async(tensor, name=None, op=None, process_set=None, prescale_f
     rows = tensor.shape[0]
     base, rem = divmod(rows, n)
     counts = [base + (1 if r < rem else 0) for r in range(n)]
+    if tensor.is_cuda and process_set is None and rem == 0 and op.value in (0, 1):
+        symm = _state.get_symm()
+        per = tensor.numel() // n
+        if symm is not None and symm.supports(tensor.dtype) and per > 0 and \
+                (per * tensor.element_size()) % 16 == 0:
+            # rank r reads only chunk r of every peer (or the NVSwitch sums it): S*(N-1)/N bytes, not 2S
+            src = tensor.contiguous()
+            out = torch.empty((base,) + tuple(tensor.shape[1:]), dtype=tensor.dtype, device=tensor.device)
+            scale = prescale_factor * postscale_factor / (n if op is Average else 1)
+            ev = symm.reducescatter(src, out, scale)
+            return _handles.add(_Handle(out, event=ev, name=name))
     full = tensor.clone()
     if prescale_factor != 1.0:
         full.mul_(prescale_factor)

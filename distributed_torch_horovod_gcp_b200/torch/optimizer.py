@@ -260,10 +260,10 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             w = t.to(wire)
             h = mpi_ops.allreduce_async_(w, name=name, op=self._op, prescale_factor=prescale,
                                          postscale_factor=postscale,
-                                         process_set=self._process_set)
+                                         process_set=self._process_set, _lane=1)
             return ("cast", h, w, t)
         h = mpi_ops.allreduce_async_(t, name=name, op=self._op, prescale_factor=prescale,
-                                     postscale_factor=postscale, process_set=self._process_set)
+                                     postscale_factor=postscale, process_set=self._process_set, _lane=1)
         return ("plain", h, None, t)
 
     def synchronize(self):
