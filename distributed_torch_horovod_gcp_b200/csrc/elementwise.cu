@@ -669,6 +669,69 @@ int b200dp_bn_fwd(const void* x, const void* res, void* y, const void* gamma, co
   return 0;
 }
 
+// ---- SyncBatchNorm building blocks: the same kernels with the cross-rank reduction between the passes ----
+// local statistics only: stats[2*C] = sum | sum of squares over this rank's M rows
+int b200dp_bn_stats(const void* x, float* stats, long long M, int C, unsigned long long stream) {
+  if (!shape_ok(C)) return -1;
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C, st);
+  if (e != cudaSuccess) return fail("memset", e);
+  bn_stats_kernel<<<reduce_grid(), RTHREADS, 0, st>>>((const uint4*)x, stats, stats + C, (long long)M * (C / 8),
+                                                      C / 8);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("bn_stats launch", e);
+  return 0;
+}
+
+// finalize + apply with statistics that were summed over all ranks: `count` = global number of rows
+int b200dp_bn_fwd_sync(const void* x, const void* res, void* y, const void* gamma, const void* beta,
+                       const float* stats, float* mean, float* invstd, float* a, float* b, void* running_mean,
+                       void* running_var, long long M_local, double count, int C, float eps, float momentum,
+                       int relu, int param_bf16, void* relu_mask, unsigned long long stream) {
+  if (!shape_ok(C)) return -1;
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  const int V = C / 8;
+  const long long nvec = M_local * V;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, stats + C, gamma, beta, mean, invstd, a, b,
+                                                      running_mean, running_var, (float)count, eps, momentum, C,
+                                                      param_bf16);
+  bn_apply_kernel<<<grid_for(nvec, V), THREADS, 0, st>>>((const uint4*)x, (const uint4*)res, (uint4*)y, a, b, nvec,
+                                                         V, relu, (uint8_t*)relu_mask);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("bn_fwd_sync launch", e);
+  return 0;
+}
+
+// backward, pass 1: local sums[2*C] = sum dz | sum dz*(x - mean)     (dz = dy masked by the ReLU)
+int b200dp_bn_bwd_reduce(const void* dy, const void* x, const void* relu_mask, const float* mean, float* sums,
+                         long long M, int C, int relu, unsigned long long stream) {
+  if (!shape_ok(C)) return -1;
+  cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
+  cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(float) * 2 * C, st);
+  if (e != cudaSuccess) return fail("memset", e);
+  bn_bwd_reduce_kernel<<<reduce_grid(), RTHREADS, 0, st>>>((const uint4*)dy, (const uint4*)x,
+                                                           (const uint8_t*)relu_mask, mean, sums, sums + C,
+                                                           (long long)M * (C / 8), C / 8, relu);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("bn_bwd_reduce launch", e);
+  return 0;
+}
+
+// backward, pass 2 with globally summed `sums` and the global row count
+int b200dp_bn_bwd_apply(const void* dy, const void* x, const void* relu_mask, void* dx, void* dres,
+                        const float* scale_a, const float* mean, const float* invstd, const float* sums,
+                        double count, long long M, int C, int relu, unsigned long long stream) {
+  if (!shape_ok(C)) return -1;
+  const int V = C / 8;
+  const long long nvec = M * V;
+  bn_bwd_apply_kernel<<<grid_for(nvec, V), THREADS, 0, (cudaStream_t)(uintptr_t)stream>>>(
+      (const uint4*)dy, (const uint4*)x, (const uint8_t*)relu_mask, (uint4*)dx, (uint4*)dres, mean, invstd, scale_a,
+      sums, sums + C, (float)(1.0 / count), nvec, V, relu, nullptr, nullptr, 0);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("bn_bwd_apply launch", e);
+  return 0;
+}
+
 // Inference / frozen-statistics apply: y = relu(x*a + b + res) with caller-provided a, b.
 int b200dp_bn_apply(const void* x, const void* res, void* y, const float* a, const float* b, long long M,
                     int C, int relu, unsigned long long stream) {

@@ -269,3 +269,226 @@ def watchdog_timeout(hvd):
     else:
         time.sleep(6)
     return raised or r == 1
+
+
+def native_collectives_match_nccl(hvd):
+    """reduce-scatter / all-gather / all-to-all on the sm_100a kernels vs torch.distributed (NCCL)."""
+    s = _symm(hvd)
+    r, n = hvd.rank(), hvd.size()
+    dev = s.device
+    launches0 = s.launches
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 2e-2)):
+        for rows in (n * 8, n * 1024, n * 40000):
+            torch.manual_seed(rows + r)
+            x = torch.randn(rows, 16, device=dev).to(dtype)
+            # reduce-scatter (Average and Sum)
+            ref = x.float().clone()
+            dist.all_reduce(ref)
+            per = rows // n
+            for op, scale in ((hvd.Sum, 1.0), (hvd.Average, 1.0 / n)):
+                out = hvd.reducescatter(x, op=op)
+                want = ref[r * per:(r + 1) * per] * scale
+                assert out.shape == want.shape
+                err = (out.float() - want).abs().max().item() / max(want.abs().max().item(), 1e-6)
+                assert err < tol, ("reducescatter", dtype, rows, err)
+            # all-gather
+            g = hvd.allgather(x)
+            refs = [torch.empty_like(x) for _ in range(n)]
+            dist.all_gather(refs, x)
+            assert torch.equal(g, torch.cat(refs, dim=0)), ("allgather", dtype, rows)
+            # all-to-all (equal splits)
+            a = hvd.alltoall(x)
+            ins = list(x.chunk(n, dim=0))
+            outs = [torch.empty_like(c) for c in ins]
+            dist.all_to_all(outs, ins)
+            assert torch.equal(a, torch.cat(outs, dim=0)), ("alltoall", dtype, rows)
+    assert s.launches - launches0 >= 2 * 3 * 4, "native kernels did not run"
+    # ragged all-gather keeps Horovod semantics (fallback path)
+    t = torch.full((r + 1, 3), float(r), device=dev)
+    g = hvd.allgather(t)
+    assert g.shape[0] == n * (n + 1) // 2
+    torch.cuda.synchronize()
+    s.check_errors()
+    return True
+
+
+def sync_bn_kernel_path(hvd):
+    """SyncBatchNorm on NHWC bf16: fused BN kernels + one-shot allreduce == fp32 BN over the global batch."""
+    s = _symm(hvd)
+    r, n = hvd.rank(), hvd.size()
+    dev = s.device
+    from distributed_torch_horovod_gcp_b200.ops import counters, kernels
+    assert kernels.has("bn_act")
+    torch.manual_seed(5)
+    C = 64
+    full = torch.randn(n * 4, C, 8, 8, device=dev)
+    gfull = torch.randn(n * 4, C, 8, 8, device=dev)
+    bn = hvd.SyncBatchNorm(C).to(dev).to(torch.bfloat16)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C) + 0.5)
+        bn.bias.copy_(torch.randn(C) * 0.1)
+    x = full[r * 4:(r + 1) * 4].to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = bn(x)
+    y.backward(gfull[r * 4:(r + 1) * 4].to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+    # oracle: plain BN in fp32 over the whole batch (bf16-rounded inputs)
+    ref = torch.nn.BatchNorm2d(C).to(dev)
+    with torch.no_grad():
+        ref.weight.copy_(bn.weight.float())
+        ref.bias.copy_(bn.bias.float())
+    xf = full.to(torch.bfloat16).float().requires_grad_(True)
+    yr = ref(xf)
+    yr.backward(gfull.to(torch.bfloat16).float())
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-6)).item()
+    assert rel(y, yr[r * 4:(r + 1) * 4]) < 1e-2
+    assert rel(x.grad, xf.grad[r * 4:(r + 1) * 4]) < 2e-2
+    # local parameter gradients sum (over ranks) to the global ones
+    gw = hvd.allreduce(bn.weight.grad.float(), op=hvd.Sum)
+    assert rel(gw, ref.weight.grad) < 2e-2
+    assert rel(bn.running_var.float(), ref.running_var) < 2e-2
+    s.check_errors()
+    return True
+
+
+def fused_engine_cuda_graph(hvd):
+    """The headline path: fused engine + whole-step CUDA graph at N > 1 trains like the eager fused path."""
+    from distributed_torch_horovod_gcp_b200.models import resnet18
+    from distributed_torch_horovod_gcp_b200.utils.graph import GraphedStep
+    s = _symm(hvd)
+    r, n = hvd.rank(), hvd.size()
+    dev = s.device
+    losses = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0)
+        m = resnet18(num_classes=10).to(dev).to(torch.bfloat16).to(memory_format=torch.channels_last)
+        opt = hvd.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.02, momentum=0.9),
+                                       named_parameters=m.named_parameters())
+        hvd.broadcast_parameters(m.state_dict(), root_rank=0)
+        assert opt.fused_engine is not None
+        torch.manual_seed(10 + r)
+        x = torch.randn(8, 3, 64, 64, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        y = torch.randint(0, 10, (8,), device=dev)
+
+        def step(x, y):
+            loss = F.cross_entropy(m(x).float(), y)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+            return loss.detach()
+        fn = GraphedStep(step, [x, y], warmup=2) if mode == "graph" else step
+        ls = [float(fn(x, y)) for _ in range(6)]
+        torch.cuda.synchronize()
+        assert all(l == l for l in ls), ls
+        # replicas stay bit-identical
+        flat = torch.cat([p.detach().float().reshape(-1) for p in m.parameters()])
+        g = [torch.empty_like(flat) for _ in range(n)]
+        dist.all_gather(g, flat)
+        assert all(torch.equal(g[0], q) for q in g), mode
+        losses[mode] = ls
+        opt.remove_hooks()
+    # graph warm-up consumed 3 extra steps (2 warm-up + capture): the loss must keep decreasing
+    assert losses["eager"][-1] < losses["eager"][0]
+    assert losses["graph"][-1] < losses["eager"][0]
+    s.check_errors()
+    return losses
+
+
+def model_to_after_wrap(hvd):
+    """`model.to(device)` AFTER DistributedOptimizer re-flattens nn.LSTM weights into a
+    fresh cuDNN buffer; the engine must notice and re-home them, and the LSTM weights must train."""
+    from distributed_torch_horovod_gcp_b200.models import LSTM
+    s = _symm(hvd)
+    r, n = hvd.rank(), hvd.size()
+    dev = s.device
+    torch.manual_seed(0)
+    m = LSTM(23, 10, 1, 256, device=dev)
+    ref = copy.deepcopy(m)
+    opt = hvd.DistributedOptimizer(torch.optim.Adam(m.parameters(), lr=1e-3),
+                                   named_parameters=m.named_parameters())
+    m.to(dev)                                   # reference order: app/torch_train.py:259 then :261
+    ropt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+    hvd.broadcast_parameters(m.state_dict(), root_rank=0)
+    w0 = m.lstm.weight_hh_l0.detach().clone()
+    for step in range(3):
+        torch.manual_seed(100 + step * n + r)
+        x, y = torch.randn(32, 10, 23, device=dev), torch.randn(32, 1, 1, device=dev)
+        for mod, o, is_ref in ((m, opt, False), (ref, ropt, True)):
+            torch.manual_seed(7 + step * n + r)
+            F.mse_loss(mod(x), y).backward()
+            if is_ref:
+                for p in mod.parameters():
+                    dist.all_reduce(p.grad)
+                    p.grad /= n
+            o.step()
+            o.zero_grad()
+    torch.cuda.synchronize()
+    assert not torch.equal(m.lstm.weight_hh_l0, w0), "LSTM weights were never updated"
+    for (na, a), b in zip(m.named_parameters(), ref.parameters()):
+        torch.testing.assert_close(a, b, rtol=2e-2, atol=2e-5, msg=na)
+    s.check_errors()
+    return opt.fused_engine.rehomed
+
+
+def init_shutdown_cycles(hvd):
+    """init -> train -> shutdown -> init twice in one process: symmetric memory is released each time."""
+    from distributed_torch_horovod_gcp_b200 import _state
+    free0 = None
+    for cycle in range(3):
+        s = _symm(hvd)
+        dev = s.device
+        m = torch.nn.Linear(512, 512).to(dev)
+        opt = hvd.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.1),
+                                       named_parameters=m.named_parameters())
+        assert opt.fused_engine is not None
+        for _ in range(2):
+            m(torch.randn(4, 512, device=dev)).sum().backward()
+            opt.step()
+            opt.zero_grad()
+        t = torch.full((1024,), float(hvd.rank()), device=dev)
+        assert float(hvd.allreduce(t, op=hvd.Sum)[0]) == sum(range(hvd.size()))
+        torch.cuda.synchronize()
+        s.check_errors()
+        opt.remove_hooks()
+        hvd.shutdown()
+        assert float(m.weight.sum()) == float(m.weight.sum())       # parameters survive the release
+        free, _ = torch.cuda.mem_get_info(dev)
+        if free0 is None:
+            free0 = free
+        else:   # no 64 MiB-per-cycle staging leak (allow allocator noise)
+            assert free0 - free < (48 << 20), (cycle, free0, free)
+        hvd.init()
+    return True
+
+
+def allreduce_large(hvd):
+    """256 MiB and 1 GiB fp32 buckets through every algorithm (NVLS tail path included) vs NCCL."""
+    s = _symm(hvd)
+    from distributed_torch_horovod_gcp_b200.runtime import symm as S
+    r, n = hvd.rank(), hvd.size()
+    dev = s.device
+    for numel in ((64 << 20) + 4, (256 << 20)):
+        t = hvd.symm_empty(numel, torch.float32)
+        torch.manual_seed(r)
+        base = torch.randn(1 << 20, device=dev)
+        t.view(-1)[: (numel // (1 << 20)) * (1 << 20)].view(-1, 1 << 20).copy_(base.expand(numel // (1 << 20), -1))
+        t.view(-1)[(numel // (1 << 20)) * (1 << 20):] = 1.0
+        ref = base.clone()
+        dist.all_reduce(ref)
+        for algo in ("twoshot", "nvls"):
+            if algo == "nvls" and not s.multicast:
+                continue
+            code = {"twoshot": S.ALGO_TWOSHOT, "nvls": S.ALGO_NVLS}[algo]
+            y = t.clone() if False else t      # in place in symmetric memory
+            snap = y.view(-1)[:8].clone()
+            ev = s.allreduce_(y, algo=code)
+            ev.synchronize()
+            got = y.view(-1)[: 1 << 20]
+            err = (got - ref).abs().max().item() / ref.abs().max().item()
+            assert err < 1e-5, (numel, algo, err)
+            tail = y.view(-1)[-4:]
+            assert torch.allclose(tail, torch.full_like(tail, float(n))), (numel, algo, tail)
+            # restore the inputs for the next algorithm
+            t.view(-1)[: (numel // (1 << 20)) * (1 << 20)].view(-1, 1 << 20).copy_(base.expand(numel // (1 << 20), -1))
+            t.view(-1)[(numel // (1 << 20)) * (1 << 20):] = 1.0
+        del t
+    s.check_errors()
+    return True

@@ -52,3 +52,29 @@ def test_watchdog_reports_missing_rank(monkeypatch):
     monkeypatch.setenv("B200DP_KERNEL_TIMEOUT_S", "3")
     res = run_workers(2, "gpu_cases", "watchdog_timeout", cuda=True, timeout=300)
     assert all(res)
+
+
+def test_native_collectives_match_nccl():
+    assert all(run_workers(_world(), "gpu_cases", "native_collectives_match_nccl", cuda=True, timeout=600))
+
+
+def test_sync_bn_kernel_path():
+    assert all(run_workers(_world(), "gpu_cases", "sync_bn_kernel_path", cuda=True, timeout=300))
+
+
+def test_fused_engine_cuda_graph():
+    res = run_workers(_world(), "gpu_cases", "fused_engine_cuda_graph", cuda=True, timeout=600)
+    print("losses:", res[0])
+
+
+def test_model_to_after_wrap():
+    res = run_workers(_world(), "gpu_cases", "model_to_after_wrap", cuda=True, timeout=300)
+    assert all(r >= 1 for r in res), res      # the engine had to re-home at least one parameter
+
+
+def test_init_shutdown_cycles():
+    assert all(run_workers(_world(), "gpu_cases", "init_shutdown_cycles", cuda=True, timeout=600))
+
+
+def test_allreduce_large():
+    assert all(run_workers(_world(), "gpu_cases", "allreduce_large", cuda=True, timeout=900))
