@@ -11,9 +11,11 @@ moves the same 10 tensors / 1 480 196 bytes.
 B200-first changes:
   * ``(h0, c0)`` come from the device generator (no CPU randn + pageable H2D + sync per
     step), the last-step gather is a slice (no host-built index tensor);
-  * on CUDA, when the in-tree kernels are built, forward/backward run as the persistent
-    fused LSTM kernel (K5) and the chained-GEMM head (K6) from ``ops.lstm_fused``; cuDNN /
-    cuBLAS remain the fallback and the numerics oracle.
+  * on CUDA (fp32, hidden size 256, one unidirectional layer — the reference configuration)
+    forward/backward run on the persistent cluster LSTM kernels (K5: ``ops/lstm_rec.py``,
+    csrc/lstm_rec_sm100.cu — tf32 tcgen05, W_hh resident in shared memory, h exchanged through
+    DSMEM) and the chained-GEMM head (K6: ``ops/lstm_fused.py``); other shapes (bidirectional,
+    multi-layer, other hidden sizes) use cuDNN / cuBLAS, which is also the numerics oracle.
 """
 from __future__ import annotations
 

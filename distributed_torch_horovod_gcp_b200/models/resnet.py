@@ -61,11 +61,13 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         identity = x
-        out = F2.conv_bn_act(x, self.conv1, self.bn1, relu=True)
+        # identity blocks: the skip gradient is handed to conv1's dgrad epilogue instead of a separate add
+        box = F2.new_grad_box(x) if self.downsample is None else None
+        out = F2.conv_bn_act(x, self.conv1, self.bn1, relu=True, input_box=box)
         out = F2.conv_bn_act(out, self.conv2, self.bn2, relu=True)
         if self.downsample is not None:
             identity = F2.conv_bn_act(x, self.downsample[0], self.downsample[1], relu=False)
-        return F2.conv_bn_act(out, self.conv3, self.bn3, relu=True, residual=identity)
+        return F2.conv_bn_act(out, self.conv3, self.bn3, relu=True, residual=identity, skip_box=box)
 
 
 class ResNet(nn.Module):

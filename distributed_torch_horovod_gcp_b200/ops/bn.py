@@ -67,7 +67,7 @@ class _BNActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, residual, relu, eps, momentum,
-                stats_in=None):
+                stats_in=None, box=None):
         N, C, H, W = x.shape
         M = N * H * W
         dev = x.device
@@ -92,6 +92,7 @@ class _BNActFn(torch.autograd.Function):
         ctx.save_for_backward(x, mask, mean, invstd, a)
         ctx.relu, ctx.has_res, ctx.pdtype = relu, residual is not None, gamma.dtype
         ctx.affine = (gamma, beta)
+        ctx.box = box
         if ctx.needs_input_grad[1]:
             grad_sink.note_forward(gamma)
         if ctx.needs_input_grad[2]:
@@ -134,11 +135,14 @@ class _BNActFn(torch.autograd.Function):
             dgamma, dbeta = dgb[:C], dgb[C:]              # written by the kernel in the param dtype
         if ctx.has_res and dres is None:
             dres = dy                       # no ReLU: the residual branch gets dy unchanged
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+        if ctx.has_res and ctx.box is not None and ctx.box.armed:
+            ctx.box.dres = dres             # picked up by the block's first conv (dgrad epilogue adds it)
+            dres = None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
 
 
 def bn_act(x, bn: torch.nn.BatchNorm2d, relu: bool, residual: Optional[torch.Tensor] = None,
-           stats: Optional[torch.Tensor] = None):
+           stats: Optional[torch.Tensor] = None, box=None):
     if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
         residual = residual.contiguous(memory_format=torch.channels_last)
     if bn.training:
@@ -146,7 +150,7 @@ def bn_act(x, bn: torch.nn.BatchNorm2d, relu: bool, residual: Optional[torch.Ten
             bn.num_batches_tracked.add_(1)
         mom = bn.momentum if bn.momentum is not None else 0.1
         return _BNActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
-                              relu, bn.eps, mom, stats)
+                              relu, bn.eps, mom, stats, box)
     # inference: frozen statistics -> one fused apply pass
     a = (bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps))
     b = bn.bias.float() - bn.running_mean.float() * a
@@ -218,13 +222,13 @@ def _is_stem_conv(x, conv) -> bool:
             and x.shape[2] % 2 == 0 and x.shape[3] % 8 == 0 and conv.out_channels % 8 == 0)
 
 
-def conv2d(x, conv: torch.nn.Conv2d):
+def conv2d(x, conv: torch.nn.Conv2d, box=None):
     """Convolution of an NHWC bf16 activation; 1x1/stride-1 and the 7x7 stem -> tcgen05 GEMM."""
     w = conv.weight
     if _is_gemm_conv(x, conv):
         N, C, H, W = x.shape
         x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, C)             # view: NHWC rows
-        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C), owner=w)     # [M, Cout]
+        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C), owner=w, box=box)     # [M, Cout]
         return y2.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2)      # logical NCHW, NHWC memory
     if _is_stem_conv(x, conv):
         return _StemConvFn.apply(x, w)
@@ -234,12 +238,14 @@ def conv2d(x, conv: torch.nn.Conv2d):
     return F.conv2d(x, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
 
 
-def conv_bn_act(x, conv, bn, relu: bool, residual=None):
-    y = conv2d(x, conv)
+def conv_bn_act(x, conv, bn, relu: bool, residual=None, skip_box=None, input_box=None):
+    """``input_box``: this conv consumes the block input whose skip gradient will arrive through the
+    box; ``skip_box``: this BN's residual IS that block input (grad_sink.GradBox)."""
+    y = conv2d(x, conv, box=input_box)
     C = y.shape[1]
     if bn_supported(y, C) and bn.weight is not None and \
             (residual is None or residual.dtype == torch.bfloat16):
-        return bn_act(y, bn, relu, residual)
+        return bn_act(y, bn, relu, residual, box=skip_box)
     y = bn(y)
     if residual is not None:
         y = y + residual

@@ -2,8 +2,9 @@
 
 Each function is ONE fusable unit.  ``*_reference`` are plain PyTorch compositions — the CPU
 path and the fp32 numerics oracle for the kernels' tests; the CUDA fast paths are the
-hand-written sm_100a kernels bound in ``ops.kernels`` (tcgen05 GEMM with fused epilogues,
-fused BN/ReLU/residual, LayerNorm, attention).
+hand-written sm_100a kernels bound in ``ops.kernels``: tcgen05 GEMM with fused epilogues
+(ops/gemm.py), implicit-GEMM convolution (ops/conv.py), fused BN/ReLU/residual and max-pool
+(ops/bn.py), LayerNorm (ops/ln.py), flash attention forward/backward (ops/attention.py).
 """
 from __future__ import annotations
 
@@ -36,11 +37,21 @@ def conv_bn_act_reference(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool,
 
 
 def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool = True,
-                residual: Optional[torch.Tensor] = None):
+                residual: Optional[torch.Tensor] = None, skip_box=None, input_box=None):
+    """``skip_box`` / ``input_box`` (kernel path only): see ``ops.grad_sink.GradBox`` — the block's last
+    BN parks the skip-connection gradient, the block's first conv adds it in its dgrad epilogue."""
     k = _kernels(x)
     if k is not None and k.has("conv_bn_act"):
-        return k.conv_bn_act(x, conv, bn, relu, residual)
+        return k.conv_bn_act(x, conv, bn, relu, residual, skip_box=skip_box, input_box=input_box)
     return conv_bn_act_reference(x, conv, bn, relu, residual)
+
+
+def new_grad_box(x: torch.Tensor):
+    """A GradBox when ``x`` takes the kernel path and needs a gradient, else ``None``."""
+    if _kernels(x) is None or not x.requires_grad or not torch.is_grad_enabled():
+        return None
+    from .grad_sink import GradBox
+    return GradBox()
 
 
 def max_pool_3x3_s2(x):

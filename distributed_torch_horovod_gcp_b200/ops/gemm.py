@@ -168,9 +168,12 @@ def bias_grad(dz: torch.Tensor, N: int, M: int, dtype) -> torch.Tensor:
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, act, residual, owner=None):
+    def forward(ctx, x, weight, bias, act, residual, owner=None, box=None):
         K = weight.shape[1]
         ctx.owner = owner if owner is not None else weight
+        ctx.box = box if (box is not None and ctx.needs_input_grad[0]) else None
+        if ctx.box is not None:
+            ctx.box.armed = True
         if ctx.needs_input_grad[1]:
             grad_sink.note_forward(ctx.owner)
         N = weight.shape[0]
@@ -209,13 +212,23 @@ class _LinearFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
-            gemm(dz, weight, dx, M, K, N, b_mn=True)                       # dx = dz @ W
+            skip = None
+            if ctx.box is not None and ctx.box.dres is not None:
+                skip = ctx.box.dres                 # skip-connection gradient of the same block input
+                ctx.box.dres = None
+                if skip.dim() == 4:                 # NHWC activation -> its [M, C] matrix (a view)
+                    skip = skip.permute(0, 2, 3, 1).reshape(M, K)
+                else:
+                    skip = skip.reshape(M, K)
+                if not skip.is_contiguous():
+                    skip = skip.contiguous()
+            gemm(dz, weight, dx, M, K, N, b_mn=True, residual=skip)        # dx = dz @ W (+ skip gradient)
             dx = dx.view(ctx.x_shape)
         if ctx.needs_input_grad[1]:
             dw = wgrad(dz, x2, N, K, M, weight.dtype, owner=ctx.owner)     # dW = dz^T @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = bias_grad(dz, N, M, ctx.bias_dtype)
-        return dx, dw, db, None, dres, None
+        return dx, dw, db, None, dres, None, None
 
 
 def act_backward(dy2: torch.Tensor, z: torch.Tensor, act: int) -> torch.Tensor:
@@ -344,7 +357,9 @@ def qkv_proj(x, weight, bias):
     return _QKVFn.apply(x, weight, bias)
 
 
-def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, owner=None):
+def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, owner=None, box=None):
     """``owner``: the parameter whose storage ``weight`` is a 2D view of (a 1x1 conv weight), so the
-    weight gradient can be written into its gradient-bucket slot directly."""
-    return _LinearFn.apply(x, weight, bias, ACT[act], residual, owner)
+    weight gradient can be written into its gradient-bucket slot directly.  ``box``: a
+    ``grad_sink.GradBox`` through which a later node hands this layer the skip-connection gradient of
+    the same input (added in the dgrad epilogue)."""
+    return _LinearFn.apply(x, weight, bias, ACT[act], residual, owner, box)

@@ -75,3 +75,20 @@ def begin(weight, krsc: bool = False) -> Tuple[Optional[torch.Tensor], bool, Opt
                 g.is_contiguous(memory_format=torch.channels_last)):
             return None, False, None
     return g, sink.passes_done() > 0, sink.fire
+
+
+class GradBox:
+    """Hand-off of a residual-branch gradient between two autograd nodes of one block.
+
+    In a residual block the block input ``x`` feeds the first convolution AND the skip connection, so
+    autograd sums two activation-sized gradients with a stand-alone ``add`` kernel (16 of them per
+    ResNet-50 step, ~1.1 ms).  With a box, the node that produces the skip gradient (the fused
+    BN+add+ReLU backward) parks it here instead of returning it, and the first convolution's dgrad GEMM
+    adds it in its epilogue (``C = A B + residual``) — the returned input gradient is already the sum.
+    The consumer arms the box in ITS forward (which runs first), so a producer never withholds a
+    gradient nobody will pick up."""
+    __slots__ = ("armed", "dres")
+
+    def __init__(self):
+        self.armed = False
+        self.dres = None

@@ -26,6 +26,7 @@ import torch
 import torch.distributed as dist
 
 from .. import _state
+from ..utils import nvtx
 from .buckets import Bucket, arena_sizes
 
 _ENGINES: "weakref.WeakSet[FusedEngine]" = weakref.WeakSet()
@@ -243,7 +244,11 @@ class FusedEngine:
         if tl is not None:
             s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s_ev.record(self.side)
+        if nvtx.enabled():
+            nvtx.push(f"bucket.{b.index} FUSED_ALLREDUCE_{self.S.ALGO_NAMES[self._algo[b.index]].upper()} "
+                      f"{b.nbytes / 2**20:.1f}MB")
         self.symm.launch_allreduce(a, self._algo[b.index], b.dtype, b.nbytes, self.side)
+        nvtx.pop()
         self.kernel_launches += 1
         if tl is not None:
             e_ev.record(self.side)

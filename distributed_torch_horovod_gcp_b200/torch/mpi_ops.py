@@ -181,6 +181,9 @@ def _timeline(name: str, phase: str, **kw):
     tl = _state.runtime().timeline
     if tl is not None:
         tl.mark(name or "unnamed", phase, **kw)
+    from ..utils import nvtx
+    if nvtx.enabled():
+        nvtx.mark(f"{phase} {name or 'unnamed'}")
 
 
 # ----------------------------------------------------------------------------- allreduce

@@ -35,6 +35,7 @@ import torch
 import torch.distributed as dist
 
 from .. import _state
+from ..utils import nvtx
 from ..parallel.buckets import Bucket, plan_buckets, plan_hash, arena_sizes
 from .compression import Compression
 from . import mpi_ops
@@ -328,7 +329,8 @@ class _DistributedOptimizer(torch.optim.Optimizer):
             return super(self.__class__, self).step(closure)
         tl = _state.runtime().timeline
         if tl is None:
-            return self._step_impl(closure)
+            with nvtx.range("optimizer.step"):
+                return self._step_impl(closure)
         tl.begin("optimizer", "STEP")
         try:
             return self._step_impl(closure)

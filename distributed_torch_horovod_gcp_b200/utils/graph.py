@@ -13,6 +13,8 @@ from typing import Callable, Sequence
 
 import torch
 
+from . import nvtx
+
 
 class GraphedStep:
     """``GraphedStep(fn, example_inputs)``: ``fn(*tensors) -> loss``.  Inputs are copied into
@@ -44,6 +46,7 @@ class GraphedStep:
                 raise ValueError("GraphedStep needs fixed input shapes; got "
                                  f"{tuple(t.shape)} vs captured {tuple(s.shape)}")
             s.copy_(t, non_blocking=True)
-        self.graph.replay()
+        with nvtx.range("graphed_step.replay"):
+            self.graph.replay()
         self.replays += 1
         return self.static_out
