@@ -86,6 +86,9 @@ conv_bf16_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   uint64_t* tmem_full = bars + 2 * C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  const bool want_stats = MODE == MODE_FPROP && p.g.stats != nullptr;
+  if (want_stats) stats_zero(s_stats, NUM_THREADS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -257,7 +260,7 @@ conv_bf16_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         at.n = (mt / (p.tiles_w * p.tiles_h)) * p.bn + r0 / (p.bw * p.bh);
         at.c_ptr = nullptr;
         epilogue_rows<BN>(p.g, &maps.out[cl.out_map], nullptr, tmem_base, acc, q, lane, 0, nt * BN, c_begin,
-                          c_end, my_store, at);
+                          c_end, my_store, at, want_stats ? s_stats : nullptr);
       } else {
         const int tile = w % tiles;
         const ConvTap tap = p.cls[0].taps[tile % p.num_taps_total];
@@ -273,6 +276,7 @@ conv_bf16_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (want_stats) stats_flush(p.g, s_stats, (warp - 2) * 32 + lane);
     if (MODE != MODE_WGRAD && lane == 0) tma_store_wait_all();
   }
 
@@ -307,7 +311,8 @@ struct HaloCfg {
   static constexpr int B_STAGES = (BN == 256) ? 3 : ((BN == 128) ? 6 : 8);
   static constexpr int STORE_BYTES = EPI_WARPS * 4096;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = HALO_A_STAGES * HALO_A_BYTES + B_STAGES * B_BYTES + STORE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = HALO_A_STAGES * HALO_A_BYTES + B_STAGES * B_BYTES + STORE_BYTES + 1024 + 256 +
+                                    STATS_SMEM_BYTES;
 };
 
 template <int BN, bool B_MN>
@@ -328,6 +333,9 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
   uint64_t* tmem_full = b_empty + C::B_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  const bool want_stats = !B_MN && p.g.stats != nullptr;
+  if (want_stats) stats_zero(s_stats, NUM_THREADS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -477,12 +485,13 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       at.n = mt / (p.tiles_w * p.tiles_h);
       at.c_ptr = nullptr;
       epilogue_rows<BN>(p.g, &maps.out[cl.out_map], nullptr, tmem_base, acc, q, lane, 0, nt * BN, c_begin, c_end,
-                        my_store, at);
+                        my_store, at, want_stats ? s_stats : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (want_stats) stats_flush(p.g, s_stats, (warp - 2) * 32 + lane);
     if (lane == 0) tma_store_wait_all();
   }
 
@@ -951,7 +960,7 @@ const char* b200dp_conv_last_error() { return g_err; }
 
 // y[N, OH, OW, Cout] = conv(x[N, H, W, Cin], w[Cout, R, S, Cin])          (all bf16, NHWC / KRSC)
 int b200dp_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int R, int S,
-                      int stride, int pad, int block_n, int max_ctas, unsigned long long stream) {
+                      int stride, int pad, int block_n, int max_ctas, float* stats, unsigned long long stream) {
   if (ensure_init()) return -1;
   ConvShape s{N, H, W, Cin, Cout, R, S, stride, pad, 0, 0};
   if (check_shape(s)) return -1;
@@ -962,6 +971,8 @@ int b200dp_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W
   memset(&p, 0, sizeof(p));
   init_gemm_params(p.g);
   p.g.N = Cout; p.g.K = Cin; p.g.ldc = Cout; p.g.C = y; p.g.out_mode = 0; p.g.tma_store = 1;
+  p.g.stats = stats;
+  if (stats != nullptr && Cout > STATS_MAX_N) return fail("stats: Cout <= 2048 required");
   p.g.num_n_blocks = (Cout + BN - 1) / BN;
   p.g.num_k_blocks = (Cin + BLOCK_K - 1) / BLOCK_K;
   p.kc_per_tap = p.g.num_k_blocks;

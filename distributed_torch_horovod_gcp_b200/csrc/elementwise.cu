@@ -116,14 +116,18 @@ __device__ __forceinline__ void st_param(void* p, int c, int bf16, float v) {
 }
 
 // gamma/beta/running_* are the module's tensors in their own dtype (fp32 or bf16: `pbf16`).
-__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const void* gamma,
+__global__ void bn_finalize_kernel(float* sum, float* sumsq, const void* gamma,
                                    const void* beta, float* mean, float* invstd, float* a, float* b,
                                    void* running_mean, void* running_var, float count, float eps,
-                                   float momentum, int C, int pbf16) {
+                                   float momentum, int C, int pbf16, int rezero = 0) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float m = sum[c] / count;
   const float var = fmaxf(sumsq[c] / count - m * m, 0.f);
+  if (rezero) {      // persistent accumulators filled by the producing GEMM / conv epilogue: ready for the next step
+    sum[c] = 0.f;
+    sumsq[c] = 0.f;
+  }
   const float is = rsqrtf(var + eps);
   mean[c] = m;
   invstd[c] = is;
@@ -640,7 +644,9 @@ int b200dp_cast_acc_zero(void* src, void* dst, long long n, int out_bf16, int ac
 
 int b200dp_bn_supported(int C) { return shape_ok(C) ? 1 : 0; }
 
-// stats: [2*C] fp32, zeroed by this call.  Writes mean/invstd/a/b ([C] fp32 each); updates running stats.
+// stats: [2*C] fp32, zeroed by this call (have_stats == 0), or provided by the producing GEMM / conv epilogue
+// (have_stats == 1; == 2: a persistent accumulator that the finalize kernel re-zeroes after reading).
+// Writes mean/invstd/a/b ([C] fp32 each); updates running stats.
 int b200dp_bn_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta,
                   float* stats, float* mean, float* invstd, float* a, float* b, void* running_mean,
                   void* running_var, long long M, int C, float eps, float momentum, int relu,
@@ -661,7 +667,7 @@ int b200dp_bn_fwd(const void* x, const void* res, void* y, const void* gamma, co
   }
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, stats + C, gamma, beta, mean, invstd, a, b,
                                                       running_mean, running_var, (float)M, eps, momentum, C,
-                                                      param_bf16);
+                                                      param_bf16, have_stats == 2 ? 1 : 0);
   bn_apply_kernel<<<grid, THREADS, 0, st>>>((const uint4*)x, (const uint4*)res, (uint4*)y, a, b, nvec, V,
                                             relu, (uint8_t*)relu_mask);
   e = cudaGetLastError();
@@ -692,9 +698,9 @@ int b200dp_bn_fwd_sync(const void* x, const void* res, void* y, const void* gamm
   cudaStream_t st = (cudaStream_t)(uintptr_t)stream;
   const int V = C / 8;
   const long long nvec = M_local * V;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, stats + C, gamma, beta, mean, invstd, a, b,
-                                                      running_mean, running_var, (float)count, eps, momentum, C,
-                                                      param_bf16);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(const_cast<float*>(stats), const_cast<float*>(stats) + C, gamma,
+                                                      beta, mean, invstd, a, b, running_mean, running_var,
+                                                      (float)count, eps, momentum, C, param_bf16);
   bn_apply_kernel<<<grid_for(nvec, V), THREADS, 0, st>>>((const uint4*)x, (const uint4*)res, (uint4*)y, a, b, nvec,
                                                          V, relu, (uint8_t*)relu_mask);
   cudaError_t e = cudaGetLastError();

@@ -47,6 +47,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* tmem_full = bars + 2 * C::STAGES;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  const bool want_stats = p.stats != nullptr && p.out_mode == 0 && p.tma_store;
+  if (want_stats) stats_zero(s_stats, NUM_THREADS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -172,12 +175,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epilogue_rows<BN>(p, &map_c, &map_z, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, c_begin, c_end,
-                        my_store);
+                        my_store, StoreAt{0, 0, 0, 0, nullptr}, want_stats ? s_stats : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (want_stats) stats_flush(p, s_stats, (warp - 2) * 32 + lane);
     if (p.tma_store && lane == 0) tma_store_wait_all();   // smem must outlive the bulk reads
   }
 
@@ -205,10 +209,10 @@ struct Cfg2 {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KB : this CTA's 128 rows
   static constexpr int B_BYTES = (BN2 / 2) * BLOCK_K * 2;        // 16 KB : this CTA's half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = 5;
+  static constexpr int STAGES = 4;
   static constexpr int TMEM_COLS = 2 * BN2;
   static constexpr int STORE_BYTES = EPI_WARPS * 2 * 4096;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 + 256 + STATS_SMEM_BYTES;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -270,6 +274,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   uint64_t* tmem_full = bars + 2 * C::STAGES;    // [2]        (per CTA; multicast-committed)
   uint64_t* tmem_empty = tmem_full + 2;          // [2]        (leader CTA; 8 arrivals = 2 CTAs x 4 warps)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_stats = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  const bool want_stats = p.stats != nullptr && p.out_mode == 0 && p.tma_store;
+  if (want_stats) stats_zero(s_stats, NUM_THREADS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -410,12 +417,13 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epilogue_rows<BN2>(p, &map_c, &map_z, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, c_begin, c_end,
-                         my_store);
+                         my_store, StoreAt{0, 0, 0, 0, nullptr}, want_stats ? s_stats : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_addr(&tmem_empty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (want_stats) stats_flush(p, s_stats, (warp - 2) * 32 + lane);
     if (p.tma_store && lane == 0) tma_store_wait_all();
   }
 
@@ -536,7 +544,7 @@ const char* b200dp_gemm_last_error() { return g_err; }
 int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                      int a_mn, int b_mn, const void* bias_bf16, const void* bias_f32, const void* residual,
                      void* preact, int act, int out_mode, float alpha, int splits, int block_n, int max_ctas,
-                     int two_cta, unsigned long long stream) {
+                     int two_cta, float* stats, unsigned long long stream) {
   if (ensure_init()) return -1;
   if (M <= 0 || N <= 0 || K <= 0) return fail("bad shape");
   if ((N % 8) || (lda % 8) || (ldb % 8) || (ldc % 4) || ((out_mode == 0) && (ldc % 8)))
@@ -559,6 +567,8 @@ int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K,
   }
   p.act = act; p.out_mode = out_mode; p.C = C; p.bias = bias_bf16; p.bias_f32 = bias_f32;
   p.residual = residual; p.preact = preact; p.alpha = alpha;
+  p.stats = stats;
+  if (stats != nullptr && (N > STATS_MAX_N || out_mode != 0)) return fail("stats: N <= 2048 and bf16 output required");
   p.tma_store = (out_mode == 0) ? 1 : 0;
   // B (N x K bf16) small enough to live in L2 next to the in-flight A tiles -> walk N first
   p.n_fastest = ((size_t)N * (size_t)K * 2 <= ((size_t)48 << 20)) ? 1 : 0;

@@ -31,7 +31,13 @@ struct GemmParams {
   int n_fastest;           // tile order: consecutive CTAs walk the N blocks of one M block first (A tile is
                            // fetched from HBM once and re-used from L2 while the whole B matrix stays in L2)
   float alpha;
+  float* stats;            // optional fp32 [2][N]: per-column sum | sum of squares of the bf16 OUTPUT (the batch
+                           // statistics of the BatchNorm that follows), accumulated by the epilogue
 };
+
+// Per-CTA shared-memory accumulators for GemmParams::stats: 2 * STATS_MAX_N floats after the barriers.
+constexpr int STATS_MAX_N = 2048;
+constexpr int STATS_SMEM_BYTES = 2 * STATS_MAX_N * 4;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -247,10 +253,11 @@ struct Cfg {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : ((BN == 128) ? 5 : 6);
+  static constexpr int STAGES = (BN == 256) ? 3 : ((BN == 128) ? 4 : 6);
   static constexpr int TMEM_COLS = 2 * BN;       // double-buffered fp32 accumulator
   static constexpr int STORE_BYTES = EPI_WARPS * 2 * 4096;   // per epilogue warp: out + preact staging (32 rows x 128 B each)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STORE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                                    STATS_SMEM_BYTES;
 };
 
 // Epilogue of one 32-row slab (this warp's TMEM lane quarter) of a 128 x BN accumulator: TMEM ->
@@ -268,7 +275,8 @@ template <int BN>
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtensorMap* map_c,
                                               const CUtensorMap* map_z, uint32_t tmem_base, int acc, int q,
                                               int lane, int m_row0, int n_idx, int c_begin, int c_end,
-                                              uint8_t* my_store, const StoreAt at = StoreAt{0, 0, 0, 0, nullptr}) {
+                                              uint8_t* my_store, const StoreAt at = StoreAt{0, 0, 0, 0, nullptr},
+                                              float* s_stats = nullptr) {
   const int row = m_row0 + lane;
   const bool row_ok = row < p.M;
 #pragma unroll 1
@@ -350,6 +358,30 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
         *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8(v + j * 8);
       fence_async_smem();
       __syncwarp();
+      if (s_stats != nullptr) {
+        // batch statistics of the following BatchNorm: column sums of the bf16 values just staged.  Lane l
+        // owns columns 2l, 2l+1 of this 64-column chunk and walks the 32 staged rows (one conflict-free
+        // 4-byte shared load per row: the 16-byte unit is un-swizzled per row); partials go to the CTA's
+        // shared accumulators, which are flushed to global memory ONCE per CTA.  Rows past the end of the
+        // matrix were computed from zero-filled operands and contribute nothing.
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        const uint32_t base = smem_u32(buf) + (uint32_t)((lane & 3) << 2);
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          uint32_t w;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4)));
+          const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
+          s0 += a; q0 = fmaf(a, a, q0);
+          s1 += b; q1 = fmaf(b, b, q1);
+        }
+        const int c = col0 + 2 * lane;
+        if (c < p.N) {        // N % 8 == 0: the pair is in or out together
+          atomicAdd(s_stats + c, s0);
+          atomicAdd(s_stats + c + 1, s1);
+          atomicAdd(s_stats + STATS_MAX_N + c, q0);
+          atomicAdd(s_stats + STATS_MAX_N + c + 1, q1);
+        }
+      }
       if (lane == 0) {
         if (at.rank4) {
           tma_store_4d(map_c, buf, col0, at.w, at.h, at.n);
@@ -403,6 +435,19 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
       }
       __syncwarp();
     }
+  }
+}
+
+// shared accumulators of GemmParams::stats: zero (all threads, before the kernel's first __syncthreads) and
+// flush (the 8 epilogue warps, after their tile loop: named barrier 2 among the 256 of them)
+__device__ __forceinline__ void stats_zero(float* s_stats, int nthreads) {
+  for (int i = threadIdx.x; i < 2 * STATS_MAX_N; i += nthreads) s_stats[i] = 0.f;
+}
+__device__ __forceinline__ void stats_flush(const GemmParams& p, const float* s_stats, int epi_tid) {
+  asm volatile("bar.sync 2, 256;" ::: "memory");
+  for (int c = epi_tid; c < p.N; c += EPI_WARPS * 32) {
+    atomicAdd(p.stats + c, s_stats[c]);
+    atomicAdd(p.stats + p.N + c, s_stats[STATS_MAX_N + c]);
   }
 }
 

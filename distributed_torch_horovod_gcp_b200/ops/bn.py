@@ -75,7 +75,7 @@ class _BNActFn(torch.autograd.Function):
         ws = torch.empty(6 * C, dtype=torch.float32, device=dev)
         stats, mean, invstd, a, b = ws[:2 * C], ws[2 * C:3 * C], ws[3 * C:4 * C], ws[4 * C:5 * C], ws[5 * C:]
         if stats_in is not None:
-            stats = stats_in              # accumulated by the producing GEMM's epilogue
+            stats = stats_in              # accumulated by the producing GEMM / conv epilogue (persistent buffer)
         pbf16 = int(gamma.dtype == torch.bfloat16)
         # ReLU sign bits, 1 byte per 8 channels: the backward reads 1/16th of what y would cost
         mask = torch.empty(M * (C // 8), dtype=torch.uint8, device=dev) if relu else None
@@ -86,7 +86,7 @@ class _BNActFn(torch.autograd.Function):
                                running_mean.data_ptr() if running_mean is not None else None,
                                running_var.data_ptr() if running_var is not None else None,
                                M, C, float(eps), float(momentum), int(relu), pbf16,
-                               int(stats_in is not None),
+                               2 if stats_in is not None else 0,
                                mask.data_ptr() if mask is not None else None, st))
         counters.bump("bn_fwd", 2 if stats_in is not None else 3)
         ctx.save_for_backward(x, mask, mean, invstd, a)
@@ -182,7 +182,7 @@ class _StemConvFn(torch.autograd.Function):
     on a 180 GB part, bandwidth is."""
 
     @staticmethod
-    def forward(ctx, x, weight):
+    def forward(ctx, x, weight, stats=None):
         N, C, H, W = x.shape
         OH, OW = H // 2, W // 2
         M = N * OH * OW
@@ -194,7 +194,7 @@ class _StemConvFn(torch.autograd.Function):
         wp = torch.zeros((Cout, STEM_KP), dtype=torch.bfloat16, device=x.device)
         wp[:, :147] = weight.permute(0, 2, 3, 1).reshape(Cout, 147)      # [Cout][kh][kw][c]
         y = torch.empty((M, Cout), dtype=torch.bfloat16, device=x.device)
-        _gemm.gemm(cols, wp, y, M, Cout, STEM_KP)
+        _gemm.gemm(cols, wp, y, M, Cout, STEM_KP, stats=stats)
         ctx.save_for_backward(cols)
         ctx.wshape = weight.shape
         return y.view(N, OH, OW, Cout).permute(0, 3, 1, 2)
@@ -211,7 +211,7 @@ class _StemConvFn(torch.autograd.Function):
         _gemm.gemm(dy2, cols, acc, Cout, STEM_KP, M, a_mn=True, b_mn=True, out_mode=1,
                    splits=_gemm._splits_for(Cout, STEM_KP, M))
         dw = acc[:, :147].reshape(Cout, 7, 7, 3).permute(0, 3, 1, 2).to(torch.bfloat16)
-        return None, dw.contiguous(memory_format=torch.channels_last)
+        return None, dw.contiguous(memory_format=torch.channels_last), None
 
 
 def _is_stem_conv(x, conv) -> bool:
@@ -222,30 +222,53 @@ def _is_stem_conv(x, conv) -> bool:
             and x.shape[2] % 2 == 0 and x.shape[3] % 8 == 0 and conv.out_channels % 8 == 0)
 
 
-def conv2d(x, conv: torch.nn.Conv2d, box=None):
-    """Convolution of an NHWC bf16 activation; 1x1/stride-1 and the 7x7 stem -> tcgen05 GEMM."""
+_FUSE_STATS = os.environ.get("B200DP_BN_STATS_IN_EPILOGUE", "1") == "1"
+
+
+def conv2d(x, conv: torch.nn.Conv2d, box=None, stats=None):
+    """Convolution of an NHWC bf16 activation; 1x1/stride-1 and the 7x7 stem -> tcgen05 GEMM, 3x3 and
+    strided 1x1 -> implicit-GEMM kernel.  Returns ``(y, stats_filled)``: when ``stats`` (fp32 [2*Cout]
+    accumulator) is given and the kernel that ran supports it, its epilogue has added the output's
+    per-channel sum / sum of squares."""
     w = conv.weight
     if _is_gemm_conv(x, conv):
         N, C, H, W = x.shape
         x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, C)             # view: NHWC rows
-        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C), owner=w, box=box)     # [M, Cout]
-        return y2.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2)      # logical NCHW, NHWC memory
+        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C), owner=w, box=box, stats=stats)     # [M, Cout]
+        return y2.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2), stats is not None   # logical NCHW, NHWC memory
     if _is_stem_conv(x, conv):
-        return _StemConvFn.apply(x, w)
+        return _StemConvFn.apply(x, w, stats), stats is not None
     from . import conv as _conv
     if conv.bias is None and _conv.supported(x, w, conv.stride, conv.padding, conv.dilation, conv.groups):
-        return _conv.conv2d(x, w, conv.stride[0], conv.padding[0])
-    return F.conv2d(x, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return _conv.conv2d(x, w, conv.stride[0], conv.padding[0], stats), stats is not None
+    return F.conv2d(x, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups), False
+
+
+def _stats_buffer(bn, C: int, device):
+    """Persistent per-BatchNorm accumulator (zero between steps: bn_finalize re-zeroes it after reading)."""
+    buf = getattr(bn, "_b200dp_stats", None)
+    if buf is None or buf.numel() != 2 * C or buf.device != device:
+        buf = torch.zeros(2 * C, dtype=torch.float32, device=device)
+        bn._b200dp_stats = buf
+    return buf
 
 
 def conv_bn_act(x, conv, bn, relu: bool, residual=None, skip_box=None, input_box=None):
     """``input_box``: this conv consumes the block input whose skip gradient will arrive through the
     box; ``skip_box``: this BN's residual IS that block input (grad_sink.GradBox)."""
-    y = conv2d(x, conv, box=input_box)
-    C = y.shape[1]
-    if bn_supported(y, C) and bn.weight is not None and \
-            (residual is None or residual.dtype == torch.bfloat16):
-        return bn_act(y, bn, relu, residual, box=skip_box)
+    C = conv.out_channels
+    fused_bn = _lib is not None and bn.weight is not None and bool(_lib.b200dp_bn_supported(C)) and \
+        (residual is None or residual.dtype == torch.bfloat16)
+    # batch statistics come out of the conv / GEMM epilogue (no separate pass over y)
+    want_stats = _FUSE_STATS and fused_bn and bn.training and C <= 2048 and x.dtype == torch.bfloat16
+    stats = _stats_buffer(bn, C, x.device) if want_stats else None
+    y, filled = conv2d(x, conv, box=input_box, stats=stats)
+    if stats is not None and not filled:
+        stats = None
+    if fused_bn and bn_supported(y, C):
+        return bn_act(y, bn, relu, residual, stats=stats, box=skip_box)
+    if stats is not None:
+        stats.zero_()          # filled but not consumed by the fused BN: keep the accumulator clean
     y = bn(y)
     if residual is not None:
         y = y + residual

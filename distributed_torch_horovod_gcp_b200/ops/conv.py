@@ -34,7 +34,7 @@ def register(lib, have):
         return
     _lib = lib
     vp, i, u64, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_longlong
-    lib.b200dp_conv_fprop.argtypes = [vp, vp, vp] + [i] * 11 + [u64]
+    lib.b200dp_conv_fprop.argtypes = [vp, vp, vp] + [i] * 11 + [vp, u64]
     lib.b200dp_conv_dgrad.argtypes = [vp, vp, vp] + [i] * 11 + [u64]
     lib.b200dp_conv_wgrad.argtypes = [vp, vp, vp] + [i] * 12 + [u64]
     lib.b200dp_conv_last_error.restype = ctypes.c_char_p
@@ -88,13 +88,14 @@ def _workspace(weight: torch.Tensor) -> torch.Tensor:
     return ws
 
 
-def conv_fprop(x, w_krsc, stride: int, pad: int):
+def conv_fprop(x, w_krsc, stride: int, pad: int, stats=None):
     N, Cin, H, W = x.shape
     Cout, _, R, S = w_krsc.shape
     y = torch.empty((N, Cout, H // stride, W // stride), dtype=torch.bfloat16, device=x.device,
                     memory_format=torch.channels_last)
     _ck(_lib.b200dp_conv_fprop(x.data_ptr(), w_krsc.data_ptr(), y.data_ptr(), N, H, W, Cin, Cout, R, S,
-                               stride, pad, 0, 0, torch.cuda.current_stream(x.device).cuda_stream))
+                               stride, pad, 0, 0, stats.data_ptr() if stats is not None else None,
+                               torch.cuda.current_stream(x.device).cuda_stream))
     counters.bump("conv_fprop")
     return y
 
@@ -136,11 +137,11 @@ def conv_wgrad(dy, x, weight, stride: int, pad: int) -> Optional[torch.Tensor]:
 
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, stride, pad):
+    def forward(ctx, x, weight, stride, pad, stats=None):
         w = _krsc(weight)
         if ctx.needs_input_grad[1]:
             grad_sink.note_forward(weight)
-        y = conv_fprop(x, w, stride, pad)
+        y = conv_fprop(x, w, stride, pad, stats)
         ctx.save_for_backward(x, w)
         ctx.weight = weight
         ctx.stride, ctx.pad = stride, pad
@@ -156,14 +157,16 @@ class _ConvFn(torch.autograd.Function):
             dx = conv_dgrad(dy, w, x.shape, ctx.stride, ctx.pad)
         if ctx.needs_input_grad[1]:
             dw = conv_wgrad(dy, x, ctx.weight, ctx.stride, ctx.pad)
-        return dx, dw, None, None
+        return dx, dw, None, None, None
 
 
-def conv2d(x: torch.Tensor, weight: torch.Tensor, stride: int = 1, padding: Optional[int] = None):
-    """``F.conv2d`` for NHWC bf16 activations on the sm_100a implicit-GEMM kernel."""
+def conv2d(x: torch.Tensor, weight: torch.Tensor, stride: int = 1, padding: Optional[int] = None, stats=None):
+    """``F.conv2d`` for NHWC bf16 activations on the sm_100a implicit-GEMM kernel.  ``stats`` (fp32
+    [2*Cout], zero on entry): the kernel's epilogue adds the per-channel sum / sum of squares of the
+    output to it — the batch statistics of the BatchNorm that follows."""
     if padding is None:
         padding = (weight.shape[2] - 1) // 2
-    return _ConvFn.apply(x, weight, int(stride), int(padding))
+    return _ConvFn.apply(x, weight, int(stride), int(padding), stats)
 
 
 def conv3x3(x, weight, stride: int = 1):

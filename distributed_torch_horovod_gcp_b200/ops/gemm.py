@@ -31,7 +31,7 @@ def register(lib, have):
     _lib = lib
     vp, i, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.b200dp_gemm_bf16.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, i, i, f, i,
-                                     i, i, i, ctypes.c_uint64]
+                                     i, i, i, vp, ctypes.c_uint64]
     lib.b200dp_gemm_bf16.restype = i
     lib.b200dp_gemm_last_error.restype = ctypes.c_char_p
     if hasattr(lib, "b200dp_cast_acc_zero"):
@@ -44,7 +44,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
          a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, preact: Optional[torch.Tensor] = None,
          act: int = 0, out_mode: int = 0, alpha: float = 1.0, splits: int = 1, block_n: int = 0,
-         max_ctas: int = 0, two_cta: Optional[bool] = None) -> torch.Tensor:
+         max_ctas: int = 0, two_cta: Optional[bool] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Raw kernel call.  ``a``: [M,K] (K-major) or [K,M] (MN-major) bf16 with contiguous rows;
     ``b``: [N,K] or [K,N]; ``out``: [M,N] bf16 (out_mode 0) or fp32 (1: atomic add, 2: store)."""
     assert _lib is not None, "libb200dp_kernels.so not loaded"
@@ -58,6 +58,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
         residual.data_ptr() if residual is not None else None,
         preact.data_ptr() if preact is not None else None,
         act, out_mode, float(alpha), splits, block_n, max_ctas, int(_want_2cta(M, N, K, two_cta)),
+        stats.data_ptr() if stats is not None else None,
         torch.cuda.current_stream(a.device).cuda_stream)
     if rc != 0:
         raise RuntimeError("b200dp_gemm_bf16: " + (_lib.b200dp_gemm_last_error() or b"").decode())
@@ -168,7 +169,7 @@ def bias_grad(dz: torch.Tensor, N: int, M: int, dtype) -> torch.Tensor:
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, act, residual, owner=None, box=None):
+    def forward(ctx, x, weight, bias, act, residual, owner=None, box=None, stats=None):
         K = weight.shape[1]
         ctx.owner = owner if owner is not None else weight
         ctx.box = box if (box is not None and ctx.needs_input_grad[0]) else None
@@ -189,7 +190,7 @@ class _LinearFn(torch.autograd.Function):
             r2 = residual.reshape(-1, N)
             if not r2.is_contiguous():
                 r2 = r2.contiguous()
-        gemm(x2, weight, y, M, N, K, bias=bias, residual=r2, preact=z, act=act)
+        gemm(x2, weight, y, M, N, K, bias=bias, residual=r2, preact=z, act=act, stats=stats)
         ctx.save_for_backward(x2, weight, z)
         ctx.act, ctx.has_bias, ctx.has_res = act, bias is not None, residual is not None
         ctx.x_shape = x.shape
@@ -228,7 +229,7 @@ class _LinearFn(torch.autograd.Function):
             dw = wgrad(dz, x2, N, K, M, weight.dtype, owner=ctx.owner)     # dW = dz^T @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = bias_grad(dz, N, M, ctx.bias_dtype)
-        return dx, dw, db, None, dres, None, None
+        return dx, dw, db, None, dres, None, None, None
 
 
 def act_backward(dy2: torch.Tensor, z: torch.Tensor, act: int) -> torch.Tensor:
@@ -357,9 +358,9 @@ def qkv_proj(x, weight, bias):
     return _QKVFn.apply(x, weight, bias)
 
 
-def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, owner=None, box=None):
+def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, owner=None, box=None, stats=None):
     """``owner``: the parameter whose storage ``weight`` is a 2D view of (a 1x1 conv weight), so the
     weight gradient can be written into its gradient-bucket slot directly.  ``box``: a
     ``grad_sink.GradBox`` through which a later node hands this layer the skip-connection gradient of
     the same input (added in the dgrad epilogue)."""
-    return _LinearFn.apply(x, weight, bias, ACT[act], residual, owner, box)
+    return _LinearFn.apply(x, weight, bias, ACT[act], residual, owner, box, stats)

@@ -122,7 +122,7 @@ def test_grad_sink_matches_autograd_path():
         def forward(self, x):
             from distributed_torch_horovod_gcp_b200.ops.bn import conv2d
             for c in (self.c1, self.c2, self.c3, self.c4):
-                x = torch.relu(conv2d(x, c))
+                x = torch.relu(conv2d(x, c)[0])
             return F2.linear(x.mean(dim=(2, 3)), self.fc.weight, self.fc.bias)
 
     hvd.init()
@@ -189,3 +189,33 @@ def test_bottleneck_skip_gradient_goes_through_dgrad_epilogue():
     x.grad = None
     blk(x).backward(g)
     assert _rel(x.grad, xr.grad) < 3e-2
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,hw", [(64, 256, 1, 1, 28), (64, 64, 3, 1, 28), (128, 256, 3, 1, 14),
+                                                 (128, 128, 3, 2, 28), (256, 512, 1, 2, 28), (3, 64, 7, 2, 64),
+                                                 (256, 2048, 1, 1, 7)])
+def test_bn_statistics_from_conv_epilogue(cin, cout, k, stride, hw):
+    """conv+BN(+ReLU) with the batch statistics accumulated by the conv / GEMM epilogue == the same unit
+    with the stand-alone statistics pass, for every convolution path (GEMM, implicit GEMM plain / halo,
+    strided, stem), twice in a row (the persistent accumulator is re-zeroed by the finalize kernel)."""
+    import torch.nn as nn
+    from distributed_torch_horovod_gcp_b200.ops import bn as B
+    _kern()
+    torch.manual_seed(6)
+    conv = nn.Conv2d(cin, cout, k, stride, (k - 1) // 2, bias=False).cuda().to(torch.bfloat16).to(
+        memory_format=torch.channels_last)
+    bns = [nn.BatchNorm2d(cout).cuda().to(torch.bfloat16) for _ in range(2)]
+    x = torch.randn(8, cin, hw, hw, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    outs = []
+    for fuse, bn in zip((True, False), bns):
+        B._FUSE_STATS = fuse
+        try:
+            for _ in range(2):
+                y = B.conv_bn_act(x, conv, bn, relu=True)
+        finally:
+            B._FUSE_STATS = True
+        outs.append((y.float(), bn.running_mean.float().clone(), bn.running_var.float().clone()))
+    (ya, ma, va), (yb, mb, vb) = outs
+    assert hasattr(bns[0], "_b200dp_stats") and float(bns[0]._b200dp_stats.abs().sum()) == 0.0
+    assert _rel(ya, yb) < 5e-3
+    assert _rel(ma, mb) < 1e-3 and _rel(va, vb) < 1e-3
