@@ -74,7 +74,9 @@ class FusedEngine:
         kind = _classify(opt)
         ok_dtypes = all(b.dtype in (torch.float32, torch.bfloat16, torch.float16) for b in buckets)
         devs = {b.device for b in buckets}
-        local_ok = kind is not None and ok_dtypes and len(devs) == 1 and wire_dtype is None
+        wire_ok = wire_dtype is None or (wire_dtype in (torch.bfloat16, torch.float16) and
+                                         all(b.dtype == torch.float32 for b in buckets))
+        local_ok = kind is not None and ok_dtypes and len(devs) == 1 and wire_ok
         if rt.size > 1:
             votes = [None] * rt.size
             dist.all_gather_object(votes, bool(local_ok), group=rt.cpu_group)
@@ -90,18 +92,45 @@ class FusedEngine:
             symm = LocalRuntime.get()
             if symm is None:
                 return None
-        return FusedEngine(opt, buckets, symm, kind)
+        return FusedEngine(opt, buckets, symm, kind, wire_dtype)
 
     # ------------------------------------------------------------------ construction
-    def __init__(self, opt, buckets: List[Bucket], symm, kind: str):
+    def __init__(self, opt, buckets: List[Bucket], symm, kind: str, wire_dtype=None):
         from ..runtime import symm as S
         self.S = S
         self.opt, self.buckets, self.symm, self.kind = weakref.proxy(opt), buckets, symm, kind
         self.device = buckets[0].device
         self.world = symm.world
         self.average = getattr(opt, "_op").name == "Average"
+        # Wire compression (hvd.Compression.bf16 / fp16 with fp32 parameters): gradients cross NVLink in
+        # the 16-bit wire dtype, the sum / scale / optimizer update run in fp32 inside the SAME fused
+        # kernel, on the model's own fp32 parameters (they are the kernel's "master" copy).  Every rank
+        # reduces the whole bucket (one-shot, fixed rank order) so all replicas apply the identical fp32
+        # update; the only extra work vs the uncompressed path is ONE cast pass per bucket
+        # (fp32 gradient -> wire dtype into symmetric memory), Horovod's `compress` step.
+        self.wire = wire_dtype
+        # Average with gradient_predivide_factor f: local gradients are scaled by 1/f BEFORE they are cast to
+        # the wire dtype (keeps fp16 in range), the fused kernel applies f/N after the fp32 sum.  Without
+        # wire compression the sum is fp32 end to end and (1/f)(f/N) == 1/N exactly, so nothing changes.
+        self.predivide = float(getattr(opt, "_gradient_predivide_factor", 1.0) or 1.0)
         self.arenas: Dict[torch.dtype, dict] = {}
         for (dtype, device), n in arena_sizes(buckets).items():
+            if self.wire is not None:
+                wes = torch.empty((), dtype=self.wire).element_size()
+                G = symm.alloc(n * wes)
+                P = symm.alloc(n * wes)                     # 16-bit shadow of the updated parameters (kernel output)
+                gw = G.tensor(self.wire, n)
+                gw.zero_()
+                P.tensor(self.wire, n).zero_()
+                self.arenas[dtype] = {
+                    "G": G, "P": P, "gw": gw,
+                    "g": torch.zeros(n, dtype=torch.float32, device=device),      # local fp32 gradients (autograd)
+                    "p": torch.zeros(n, dtype=torch.float32, device=device),      # the model's fp32 parameters
+                    "M": None,
+                    "S0": torch.zeros(n, dtype=torch.float32, device=device),
+                    "S1": torch.zeros(n, dtype=torch.float32, device=device) if kind != "sgd" else None,
+                }
+                continue
             es = torch.empty((), dtype=dtype).element_size()
             G = symm.alloc(n * es)
             P = symm.alloc(n * es)
@@ -187,7 +216,8 @@ class FusedEngine:
     def _make_args(self, b: Bucket):
         S, symm = self.S, self.symm
         ar = self.arenas[b.dtype]
-        es = torch.empty((), dtype=b.dtype).element_size()
+        kdtype = self.wire if self.wire is not None else b.dtype      # dtype the kernel moves over NVLink
+        es = torch.empty((), dtype=kdtype).element_size()
         off = b.flat_offset * es
         nbytes = b.numel * es
         a = S.ARArgs()
@@ -196,18 +226,25 @@ class FusedEngine:
             a.inp[r], a.out[r] = gp[r], pp[r]
         both_mc = ar["G"].mc_ptr != 0 and ar["P"].mc_ptr != 0
         algo = symm.pick_algo(nbytes, need_mc=both_mc)
+        if self.wire is not None:
+            algo = S.ALGO_ONESHOT            # every rank must hold the full fp32 update (see __init__)
         if algo == S.ALGO_NVLS and not both_mc:
             algo = S.ALGO_TWOSHOT
         if algo == S.ALGO_NVLS:
             a.in_mc, a.out_mc = ar["G"].mc_ptr + off, ar["P"].mc_ptr + off
         f32 = 4 * b.flat_offset
-        a.master = ar["M"].data_ptr() + f32 if ar["M"] is not None else 0
+        if self.wire is not None:
+            a.master = ar["p"].data_ptr() + f32      # the fp32 parameters themselves
+        else:
+            a.master = ar["M"].data_ptr() + f32 if ar["M"] is not None else 0
         a.s0 = ar["S0"].data_ptr() + f32
         a.s1 = ar["S1"].data_ptr() + f32 if ar["S1"] is not None else 0
         a.step_ctr = self.step_ctr.data_ptr() + 4 * b.index
         a.ticket = self.ticket.data_ptr() + 4 * b.index
         a.n = b.numel
         a.scale = (1.0 / self.world) if self.average else 1.0
+        if self.wire is not None and self.average and self.predivide != 1.0:
+            a.scale = self.predivide / self.world
         a.channel = S.CH_ENGINE
         a.zero_input, a.copy_back = 1, 0
         return a, algo
@@ -236,6 +273,14 @@ class FusedEngine:
         a = self._args[b.index]
         self._fill_hyper(a, self.opt.param_groups[b.group_index])
         a.lr_scale = self.lr_scale.data_ptr() if self.lr_scale is not None else 0
+        if self.wire is not None:            # compress: fp32 gradients -> wire dtype in symmetric memory
+            ar = self.arenas[b.dtype]
+            lo, hi = b.flat_offset, b.flat_offset + b.numel
+            if self.average and self.predivide != 1.0:
+                torch.mul(ar["g"][lo:hi], 1.0 / self.predivide, out=ar["gw"][lo:hi])
+            else:
+                ar["gw"][lo:hi].copy_(ar["g"][lo:hi])
+            ar["g"][lo:hi].zero_()
         cur = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
         ev.record(cur)
@@ -247,7 +292,9 @@ class FusedEngine:
         if nvtx.enabled():
             nvtx.push(f"bucket.{b.index} FUSED_ALLREDUCE_{self.S.ALGO_NAMES[self._algo[b.index]].upper()} "
                       f"{b.nbytes / 2**20:.1f}MB")
-        self.symm.launch_allreduce(a, self._algo[b.index], b.dtype, b.nbytes, self.side)
+        kdtype = self.wire if self.wire is not None else b.dtype
+        kbytes = b.numel * torch.empty((), dtype=kdtype).element_size()
+        self.symm.launch_allreduce(a, self._algo[b.index], kdtype, kbytes, self.side)
         nvtx.pop()
         self.kernel_launches += 1
         if tl is not None:
@@ -382,6 +429,7 @@ class FusedEngine:
                     except Exception:  # noqa: BLE001
                         pass
             ar["g"] = ar["p"] = ar["G"] = ar["P"] = None
+            ar["gw"] = None
         self._args.clear()
 
     def algorithms(self) -> Dict[int, str]:

@@ -492,3 +492,45 @@ def allreduce_large(hvd):
         del t
     s.check_errors()
     return True
+
+
+def compressed_engine(hvd, wire):
+    """hvd.Compression.bf16 / fp16 with fp32 parameters stays on the fused engine: 16-bit gradients on the
+    wire, fp32 sum + update inside the same kernel; result == torch optimizer on fp32-averaged gradients
+    up to the wire rounding; replicas bit-identical."""
+    s = _symm(hvd)
+    r, n = hvd.rank(), hvd.size()
+    dev = s.device
+    comp = {"bf16": hvd.Compression.bf16, "fp16": hvd.Compression.fp16}[wire]
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(300, 257), torch.nn.Tanh(), torch.nn.Linear(257, 10)).to(dev)
+    ref = copy.deepcopy(m)
+    opt = hvd.DistributedOptimizer(torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9),
+                                   named_parameters=m.named_parameters(), compression=comp,
+                                   gradient_predivide_factor=2.0)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9)
+    hvd.broadcast_parameters(m.state_dict(), root_rank=0)
+    eng = opt.fused_engine
+    assert eng is not None and eng.wire is not None, "compression must not disable the fused engine"
+    assert set(eng.algorithms().values()) == {"oneshot"}
+    for step in range(4):
+        torch.manual_seed(50 + step * n + r)
+        x, y = torch.randn(16, 300, device=dev), torch.randint(0, 10, (16,), device=dev)
+        for mod, o, is_ref in ((m, opt, False), (ref, ropt, True)):
+            F.cross_entropy(mod(x), y).backward()
+            if is_ref:
+                for p in mod.parameters():
+                    dist.all_reduce(p.grad)
+                    p.grad /= n
+            o.step()
+            o.zero_grad()
+    torch.cuda.synchronize()
+    for a, b in zip(m.parameters(), ref.parameters()):
+        assert a.dtype == torch.float32
+        torch.testing.assert_close(a, b, rtol=3e-2, atol=3e-4)
+    flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+    g = [torch.empty_like(flat) for _ in range(n)]
+    dist.all_gather(g, flat)
+    assert all(torch.equal(g[0], q) for q in g)
+    s.check_errors()
+    return True

@@ -78,3 +78,8 @@ def test_init_shutdown_cycles():
 
 def test_allreduce_large():
     assert all(run_workers(_world(), "gpu_cases", "allreduce_large", cuda=True, timeout=900))
+
+
+@pytest.mark.parametrize("wire", ["bf16", "fp16"])
+def test_compression_runs_on_the_fused_engine(wire):
+    assert all(run_workers(_world(), "gpu_cases", "compressed_engine", (wire,), cuda=True, timeout=300))

@@ -163,32 +163,37 @@ def test_grad_sink_matches_autograd_path():
 
 def test_bottleneck_skip_gradient_goes_through_dgrad_epilogue():
     """Identity bottleneck: the skip-connection gradient is added by conv1's dgrad GEMM epilogue
-    (ops.grad_sink.GradBox) — the input gradient must equal the reference composition's."""
+    (ops.grad_sink.GradBox).  Oracle: the same kernels with the box disabled (autograd's stand-alone add),
+    plus a loose check against the fp32 reference composition."""
     import copy
     from distributed_torch_horovod_gcp_b200.models.resnet import Bottleneck
-    from distributed_torch_horovod_gcp_b200.ops import functional as F2
+    from distributed_torch_horovod_gcp_b200.ops import functional as F2, counters
     _kern()
     torch.manual_seed(4)
     blk = Bottleneck(256, 64).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
     ref = copy.deepcopy(blk).float()
     x = torch.randn(8, 256, 14, 14, device="cuda").to(torch.bfloat16).contiguous(
         memory_format=torch.channels_last).requires_grad_(True)
-    xr = x.detach().float().requires_grad_(True)
     g = torch.randn(8, 256, 14, 14, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    y = blk(x)
-    y.backward(g)
+    grads = []
+    real_box = F2.new_grad_box
+    for use_box in (True, False, True):
+        F2.new_grad_box = real_box if use_box else (lambda t: None)
+        try:
+            x.grad = None
+            blk(x).backward(g)
+            grads.append(x.grad.float().clone())
+        finally:
+            F2.new_grad_box = real_box
+    assert _rel(grads[0], grads[1]) < 1e-2          # fused add == stand-alone add
+    assert _rel(grads[2], grads[1]) < 1e-2          # the box is per-forward state: second use is clean
+    xr = x.detach().float().requires_grad_(True)
     F2._FORCE_REFERENCE = True
     try:
-        yr = ref(xr)
-        yr.backward(g.float())
+        ref(xr).backward(g.float())
     finally:
         F2._FORCE_REFERENCE = False
-    assert _rel(y, yr) < 2e-2
-    assert _rel(x.grad, xr.grad) < 3e-2
-    # and a second pass (the box is per-forward state)
-    x.grad = None
-    blk(x).backward(g)
-    assert _rel(x.grad, xr.grad) < 3e-2
+    assert _rel(grads[0], xr.grad) < 1e-1           # bf16 activations / BN statistics vs fp32 end to end
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,hw", [(64, 256, 1, 1, 28), (64, 64, 3, 1, 28), (128, 256, 3, 1, 14),
