@@ -58,6 +58,7 @@ struct ConvParams {
   int bw, bh, bn;                 // pixel box: 128 rows of an M tile (fprop/dgrad) / 64 rows of a K block (wgrad)
   int tiles_w, tiles_h, tiles_n;  // boxes covering the (class) output pixel space
   int num_taps_total;             // wgrad: R*S
+  int out_w, out_h, out_n;        // extent of the (class) output pixel space: rows beyond it are clipped / not counted
   ConvClass cls[MAX_CLASSES];
 };
 struct alignas(64) ConvMaps {
@@ -259,6 +260,9 @@ conv_bf16_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         at.h = ((mt / p.tiles_w) % p.tiles_h) * p.bh + (r0 / p.bw) % p.bh;
         at.n = (mt / (p.tiles_w * p.tiles_h)) * p.bn + r0 / (p.bw * p.bh);
         at.c_ptr = nullptr;
+        at.sw = p.bw < 32 ? p.bw : 32;
+        at.sh = (32 / at.sw) < p.bh ? (32 / at.sw) : p.bh;
+        at.vw = p.out_w - at.w; at.vh = p.out_h - at.h; at.vn = p.out_n - at.n;
         epilogue_rows<BN>(p.g, &maps.out[cl.out_map], nullptr, tmem_base, acc, q, lane, 0, nt * BN, c_begin,
                           c_end, my_store, at, want_stats ? s_stats : nullptr);
       } else {
@@ -267,6 +271,7 @@ conv_bf16_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         const int mn = tile / p.num_taps_total;
         StoreAt at;
         at.rank4 = 0; at.w = at.h = at.n = 0;
+        at.sw = 32; at.sh = 1; at.vw = 32; at.vh = 1; at.vn = 1;
         at.c_ptr = reinterpret_cast<float*>(p.g.C) + tap.wcol;
         epilogue_rows<BN>(p.g, nullptr, nullptr, tmem_base, acc, q, lane, (mn / nnb) * BLOCK_M + q * 32,
                           (mn % nnb) * BN, c_begin, c_end, my_store, at);
@@ -484,6 +489,8 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       at.h = ((mt / p.tiles_w) % p.tiles_h) * HALO_BH + 4 * q;
       at.n = mt / (p.tiles_w * p.tiles_h);
       at.c_ptr = nullptr;
+      at.sw = HALO_BW; at.sh = 4;
+      at.vw = p.out_w - at.w; at.vh = p.out_h - at.h; at.vn = p.out_n - at.n;
       epilogue_rows<BN>(p.g, &maps.out[cl.out_map], nullptr, tmem_base, acc, q, lane, 0, nt * BN, c_begin, c_end,
                         my_store, at, want_stats ? s_stats : nullptr);
       tc_fence_before();
@@ -980,6 +987,7 @@ int b200dp_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W
   p.tiles_w = (s.OW + p.bw - 1) / p.bw; p.tiles_h = (s.OH + p.bh - 1) / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
   p.num_classes = 1;
   p.num_taps_total = R * S;
+  p.out_w = s.OW; p.out_h = s.OH; p.out_n = N;
   ConvClass& cl = p.cls[0];
   cl.out_map = 0;
   for (int r = 0; r < R; ++r)
@@ -1038,6 +1046,7 @@ int b200dp_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int
   choose_box(s.OW, s.OH, N, BLOCK_M, &p.bw, &p.bh, &p.bn);   // stride 2: each dx parity view is OW x OH
   p.tiles_w = (s.OW + p.bw - 1) / p.bw; p.tiles_h = (s.OH + p.bh - 1) / p.bh; p.tiles_n = (N + p.bn - 1) / p.bn;
   p.num_taps_total = R * S;
+  p.out_w = s.OW; p.out_h = s.OH; p.out_n = N;
   const bool halo = halo_enabled() && R == 3 && stride == 1 && s.OH >= 12 && s.OW >= 8 && Cin <= 128;
   if (halo) { p.bw = HALO_BW; p.bh = HALO_BH; p.bn = 1; }
   int sw, sh, sn;

@@ -119,8 +119,10 @@ __device__ __forceinline__ void st_param(void* p, int c, int bf16, float v) {
 __global__ void bn_finalize_kernel(float* sum, float* sumsq, const void* gamma,
                                    const void* beta, float* mean, float* invstd, float* a, float* b,
                                    void* running_mean, void* running_var, float count, float eps,
-                                   float momentum, int C, int pbf16, int rezero = 0) {
+                                   float momentum, int C, int pbf16, int rezero = 0,
+                                   long long* num_batches_tracked = nullptr) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked != nullptr) *num_batches_tracked += 1;   // nn.BatchNorm2d bookkeeping
   if (c >= C) return;
   const float m = sum[c] / count;
   const float var = fmaxf(sumsq[c] / count - m * m, 0.f);
@@ -650,7 +652,8 @@ int b200dp_bn_supported(int C) { return shape_ok(C) ? 1 : 0; }
 int b200dp_bn_fwd(const void* x, const void* res, void* y, const void* gamma, const void* beta,
                   float* stats, float* mean, float* invstd, float* a, float* b, void* running_mean,
                   void* running_var, long long M, int C, float eps, float momentum, int relu,
-                  int param_bf16, int have_stats, void* relu_mask, unsigned long long stream) {
+                  int param_bf16, int have_stats, void* relu_mask, void* num_batches_tracked,
+                  unsigned long long stream) {
   if (!shape_ok(C)) {
     snprintf(g_err, sizeof(g_err), "unsupported channel count %d", C);
     return -1;
@@ -667,7 +670,8 @@ int b200dp_bn_fwd(const void* x, const void* res, void* y, const void* gamma, co
   }
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, stats + C, gamma, beta, mean, invstd, a, b,
                                                       running_mean, running_var, (float)M, eps, momentum, C,
-                                                      param_bf16, have_stats == 2 ? 1 : 0);
+                                                      param_bf16, have_stats == 2 ? 1 : 0,
+                                                      (long long*)num_batches_tracked);
   bn_apply_kernel<<<grid, THREADS, 0, st>>>((const uint4*)x, (const uint4*)res, (uint4*)y, a, b, nvec, V,
                                             relu, (uint8_t*)relu_mask);
   e = cudaGetLastError();

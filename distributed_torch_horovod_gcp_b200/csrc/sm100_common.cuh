@@ -269,27 +269,57 @@ struct Cfg {
 struct StoreAt {
   int rank4, w, h, n;
   void* c_ptr;
+  // rank4 only (statistics of a convolution output): the slab is an {sw, sh, .} pixel box of which only
+  // vw x vh x vn pixels lie inside the image / batch — rows outside are computed from partly valid taps
+  // (NOT zero) and must not be counted; the TMA store clips them by itself.
+  int sw, sh, vw, vh, vn;
 };
 
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtensorMap* map_c,
                                               const CUtensorMap* map_z, uint32_t tmem_base, int acc, int q,
                                               int lane, int m_row0, int n_idx, int c_begin, int c_end,
-                                              uint8_t* my_store, const StoreAt at = StoreAt{0, 0, 0, 0, nullptr},
+                                              uint8_t* my_store, const StoreAt at = StoreAt{0, 0, 0, 0, nullptr, 32, 1, 32, 1, 1},
                                               float* s_stats = nullptr) {
   const int row = m_row0 + lane;
   const bool row_ok = row < p.M;
 #pragma unroll 1
   for (int c0 = c_begin; c0 < c_end; c0 += 64) {
     // two x32 loads in flight before the wait: 64 accumulator columns of this lane's row
+    const int col0 = n_idx + c0;
+    if (col0 >= p.N) continue;                       // warp-uniform
+    const int ncols = min(64, p.N - col0);           // N % 8 == 0 is enforced by the host
+    // Residual / auxiliary operand of this 32 x 64 slab: COALESCED 16-byte loads (a warp instruction covers
+    // 4 rows x 128 B) issued before the TMEM loads so their latency overlaps, then transposed to
+    // row-per-lane through the second (pre-activation) staging buffer.  The row-per-lane global loads
+    // this replaces touched 32 cache lines per instruction and made the dgrad GEMMs that add the
+    // skip-connection gradient LSU-bound (profiles/launches_r2_*.csv).
+    const bool res_smem = p.residual != nullptr && p.preact == nullptr && p.out_mode != 1;
+    uint4 resv[8];
+    if (res_smem) {
+      const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3), u = lane & 7;
+        resv[i] = (m_row0 + rr < p.M && u * 8 < ncols)
+                      ? *reinterpret_cast<const uint4*>(rbase + (size_t)(m_row0 + rr) * p.ldc + col0 + u * 8)
+                      : make_uint4(0, 0, 0, 0);
+      }
+    }
     uint32_t r[64];
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
     tc_ld_32x32b_x32(taddr, r);
     tc_ld_32x32b_x32(taddr + 32, r + 32);
     tc_wait_ld();
-    const int col0 = n_idx + c0;
-    if (col0 >= p.N) continue;                       // warp-uniform
-    const int ncols = min(64, p.N - col0);           // N % 8 == 0 is enforced by the host
+    if (res_smem) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3), u = lane & 7;
+        *reinterpret_cast<uint4*>(my_store + 4096 + rr * 128 + ((u ^ (rr & 7)) << 4)) = resv[i];
+      }
+      __syncwarp();
+    }
     float v[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
@@ -329,14 +359,16 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
 #pragma unroll
         for (int i = 0; i < 64; ++i) v[i] = gelu_erf(v[i]);
       }
-      if (p.residual != nullptr && row_ok) {
+      if (p.residual != nullptr && (row_ok || res_smem)) {
         const uint4* rp = reinterpret_cast<const uint4*>(
             reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldc + col0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (j * 8 < ncols) {
             float a[8];
-            unpack8(rp[j], a);
+            unpack8(res_smem ? *reinterpret_cast<const uint4*>(my_store + 4096 + lane * 128 + ((j ^ (lane & 7)) << 4))
+                             : rp[j],
+                    a);
 #pragma unroll
             for (int t = 0; t < 8; ++t) {
               if (p.act == 3) v[j * 8 + t] *= gelu_erf_grad(a[t]);
@@ -366,8 +398,14 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
         // matrix were computed from zero-filled operands and contribute nothing.
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
         const uint32_t base = smem_u32(buf) + (uint32_t)((lane & 3) << 2);
+        uint32_t rows_ok = 0xffffffffu;
+        if (at.rank4) {      // lane r decides for slab row r
+          const int rw = lane % at.sw, rh = (lane / at.sw) % at.sh, rn = lane / (at.sw * at.sh);
+          rows_ok = __ballot_sync(0xffffffffu, rw < at.vw && rh < at.vh && rn < at.vn);
+        }
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
+          if (!((rows_ok >> r) & 1u)) continue;
           uint32_t w;
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4)));
           const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);

@@ -26,7 +26,7 @@ def register(lib, have):
         return
     _lib = lib
     vp, i, f, ll, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_uint64
-    lib.b200dp_bn_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, i, i, i, vp, u64]
+    lib.b200dp_bn_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i, f, f, i, i, i, vp, vp, u64]
     lib.b200dp_bn_apply.argtypes = [vp, vp, vp, vp, vp, ll, i, i, u64]
     lib.b200dp_bn_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, ll, i, i, u64]
     lib.b200dp_bn_supported.argtypes = [i]
@@ -67,7 +67,7 @@ class _BNActFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, residual, relu, eps, momentum,
-                stats_in=None, box=None):
+                stats_in=None, box=None, nbt=None):
         N, C, H, W = x.shape
         M = N * H * W
         dev = x.device
@@ -87,7 +87,8 @@ class _BNActFn(torch.autograd.Function):
                                running_var.data_ptr() if running_var is not None else None,
                                M, C, float(eps), float(momentum), int(relu), pbf16,
                                2 if stats_in is not None else 0,
-                               mask.data_ptr() if mask is not None else None, st))
+                               mask.data_ptr() if mask is not None else None,
+                               nbt.data_ptr() if nbt is not None else None, st))
         counters.bump("bn_fwd", 2 if stats_in is not None else 3)
         ctx.save_for_backward(x, mask, mean, invstd, a)
         ctx.relu, ctx.has_res, ctx.pdtype = relu, residual is not None, gamma.dtype
@@ -138,7 +139,7 @@ class _BNActFn(torch.autograd.Function):
         if ctx.has_res and ctx.box is not None and ctx.box.armed:
             ctx.box.dres = dres             # picked up by the block's first conv (dgrad epilogue adds it)
             dres = None
-        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
 
 
 def bn_act(x, bn: torch.nn.BatchNorm2d, relu: bool, residual: Optional[torch.Tensor] = None,
@@ -146,11 +147,11 @@ def bn_act(x, bn: torch.nn.BatchNorm2d, relu: bool, residual: Optional[torch.Ten
     if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
         residual = residual.contiguous(memory_format=torch.channels_last)
     if bn.training:
-        if bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        nbt = bn.num_batches_tracked if (bn.track_running_stats and bn.num_batches_tracked is not None
+                                         and bn.num_batches_tracked.is_cuda) else None   # += 1 inside bn_finalize
         mom = bn.momentum if bn.momentum is not None else 0.1
         return _BNActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual,
-                              relu, bn.eps, mom, stats, box)
+                              relu, bn.eps, mom, stats, box, nbt)
     # inference: frozen statistics -> one fused apply pass
     a = (bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps))
     b = bn.bias.float() - bn.running_mean.float() * a
