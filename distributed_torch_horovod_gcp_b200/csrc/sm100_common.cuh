@@ -281,20 +281,23 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
                                               int lane, int m_row0, int n_idx, int c_begin, int c_end,
                                               uint8_t* my_store, const StoreAt at = StoreAt{0, 0, 0, 0, nullptr, 32, 1, 32, 1, 1},
                                               float* s_stats = nullptr) {
+  // A 64-column chunk (one 128-byte bf16 row per lane, one TMA store box) is produced in two 32-column
+  // halves: 32 accumulator values + 32 results live per thread instead of 64 + 64 — the previous
+  // single-pass version spilled ~300 B per thread at the 168-register budget of a 320-thread CTA, and the
+  // epilogue, not the MMA, bounds every K <= 512 GEMM / convolution here.
   const int row = m_row0 + lane;
   const bool row_ok = row < p.M;
+  const bool to_tma = p.out_mode == 0 && p.tma_store;
+  const bool z_tma = p.preact != nullptr && to_tma;
+  const bool res_smem = p.residual != nullptr && p.preact == nullptr && p.out_mode != 1;
 #pragma unroll 1
   for (int c0 = c_begin; c0 < c_end; c0 += 64) {
-    // two x32 loads in flight before the wait: 64 accumulator columns of this lane's row
     const int col0 = n_idx + c0;
     if (col0 >= p.N) continue;                       // warp-uniform
     const int ncols = min(64, p.N - col0);           // N % 8 == 0 is enforced by the host
-    // Residual / auxiliary operand of this 32 x 64 slab: COALESCED 16-byte loads (a warp instruction covers
-    // 4 rows x 128 B) issued before the TMEM loads so their latency overlaps, then transposed to
-    // row-per-lane through the second (pre-activation) staging buffer.  The row-per-lane global loads
-    // this replaces touched 32 cache lines per instruction and made the dgrad GEMMs that add the
-    // skip-connection gradient LSU-bound (profiles/launches_r2_*.csv).
-    const bool res_smem = p.residual != nullptr && p.preact == nullptr && p.out_mode != 1;
+    // Residual / auxiliary operand of the slab: COALESCED 16-byte loads (a warp instruction covers 4 rows
+    // x 128 B), issued before the TMEM loads so that their latency overlaps, then transposed to
+    // row-per-lane through the second (pre-activation) staging buffer.
     uint4 resv[8];
     if (res_smem) {
       const __nv_bfloat16* rbase = reinterpret_cast<const __nv_bfloat16*>(p.residual);
@@ -306,13 +309,11 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
                       : make_uint4(0, 0, 0, 0);
       }
     }
-    uint32_t r[64];
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
-    tc_ld_32x32b_x32(taddr, r);
-    tc_ld_32x32b_x32(taddr + 32, r + 32);
-    tc_wait_ld();
-    if (res_smem) {
+    if (to_tma || p.out_mode == 1) {
+      if (lane == 0) tma_store_wait_read<0>();       // the previous chunk's bulk stores have read the staging
       __syncwarp();
+    }
+    if (res_smem) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + (lane >> 3), u = lane & 7;
@@ -320,82 +321,125 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
       }
       __syncwarp();
     }
-    float v[64];
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int hc = half * 32;                      // first column of this half inside the chunk
+      if (hc >= ncols) break;                        // warp-uniform
+      const int hcols = min(32, ncols - hc);
+      uint32_t r[32];
+      tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0 + hc), r);
+      tc_wait_ld();
+      float v[32];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-    // NOTE: everything in this block that is warp-collective (__syncwarp, staging) must be reached by
-    // all 32 lanes, so only the per-row global accesses are predicated on row_ok.
-    if (p.out_mode != 1) {
-      if (p.bias != nullptr) {
-        const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0;
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+      if (p.out_mode != 1) {
+        if (p.bias != nullptr) {
+          const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0 + hc;
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i < ncols) v[i] += __bfloat162float(b[i]);
-      } else if (p.bias_f32 != nullptr) {
-        const float* b = reinterpret_cast<const float*>(p.bias_f32) + col0;
+          for (int i = 0; i < 32; ++i)
+            if (i < hcols) v[i] += __bfloat162float(b[i]);
+        } else if (p.bias_f32 != nullptr) {
+          const float* b = reinterpret_cast<const float*>(p.bias_f32) + col0 + hc;
 #pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (i < ncols) v[i] += b[i];
-      }
-      if (p.preact != nullptr && !(p.out_mode == 0 && p.tma_store) && row_ok) {
-        uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.preact) +
-                                             (size_t)row * p.ldc + col0);
+          for (int i = 0; i < 32; ++i)
+            if (i < hcols) v[i] += b[i];
+        }
+        if (p.preact != nullptr) {
+          if (z_tma) {            // pre-activation tile -> second staging buffer (stored by TMA with the output)
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j * 8 < ncols) pp[j] = pack8(v + j * 8);
-      }
-      if (p.preact != nullptr && p.out_mode == 0 && p.tma_store) {
-        // pre-activation tile -> second staging buffer (stored by TMA together with the output)
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(my_store + 4096 + lane * 128 + (((half * 4 + j) ^ (lane & 7)) << 4)) =
+                  pack8(v + j * 8);
+          } else if (row_ok) {
+            uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.preact) +
+                                                 (size_t)row * p.ldc + col0 + hc);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(my_store + 4096 + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8(v + j * 8);
-      }
-      if (p.act == 1) {
+            for (int j = 0; j < 4; ++j)
+              if (j * 8 < hcols) pp[j] = pack8(v + j * 8);
+          }
+        }
+        if (p.act == 1) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.0f);
-      } else if (p.act == 2) {
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+        } else if (p.act == 2) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) v[i] = gelu_erf(v[i]);
-      }
-      if (p.residual != nullptr && (row_ok || res_smem)) {
-        const uint4* rp = reinterpret_cast<const uint4*>(
-            reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldc + col0);
+          for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (p.residual != nullptr && (row_ok || res_smem)) {
+          const uint4* rp = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldc + col0 + hc);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j * 8 < ncols) {
-            float a[8];
-            unpack8(res_smem ? *reinterpret_cast<const uint4*>(my_store + 4096 + lane * 128 + ((j ^ (lane & 7)) << 4))
-                             : rp[j],
-                    a);
+          for (int j = 0; j < 4; ++j) {
+            if (j * 8 < hcols) {
+              float a[8];
+              unpack8(res_smem ? *reinterpret_cast<const uint4*>(my_store + 4096 + lane * 128 +
+                                                                 (((half * 4 + j) ^ (lane & 7)) << 4))
+                               : rp[j],
+                      a);
 #pragma unroll
-            for (int t = 0; t < 8; ++t) {
-              if (p.act == 3) v[j * 8 + t] *= gelu_erf_grad(a[t]);
-              else if (p.act == 4) v[j * 8 + t] = a[t] > 0.0f ? v[j * 8 + t] : 0.0f;
-              else v[j * 8 + t] += a[t];
+              for (int t = 0; t < 8; ++t) {
+                if (p.act == 3) v[j * 8 + t] *= gelu_erf_grad(a[t]);
+                else if (p.act == 4) v[j * 8 + t] = a[t] > 0.0f ? v[j * 8 + t] : 0.0f;
+                else v[j * 8 + t] += a[t];
+              }
             }
           }
         }
       }
-    }
-    if (p.out_mode == 0 && p.tma_store) {
-      // stage 32 rows x 128 B in the 128B-swizzled layout (conflict-free 16 B stores), then one
-      // lane issues a bulk tensor store; TMA clips rows >= M and columns >= N.
-      uint8_t* buf = my_store;
-      if (lane == 0) tma_store_wait_read<0>();           // previous chunk's bulk stores have read the staging
-      __syncwarp();
+      if (to_tma) {
+        // this half of the 32 x 128 B swizzled staging rows (conflict-free 16-byte stores)
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = pack8(v + j * 8);
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(my_store + lane * 128 + (((half * 4 + j) ^ (lane & 7)) << 4)) = pack8(v + j * 8);
+      } else if (p.out_mode == 1) {
+        // split-K accumulation: transpose the 32 x 32 fp32 half through the staging buffer so that a
+        // warp-level RED covers four 128-byte row segments with 16-byte vectors (red.global.add.v4.f32)
+        float* stage = reinterpret_cast<float*>(my_store);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        float* cbase = reinterpret_cast<float*>(at.c_ptr ? at.c_ptr : p.C);
+        const int ch = lane & 7;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3);
+          const float4 t = *reinterpret_cast<const float4*>(stage + rr * 32 + ((ch ^ (rr & 7)) << 2));
+          if (m_row0 + rr < p.M && ch * 4 < hcols) {
+            float* dst = cbase + (size_t)(m_row0 + rr) * p.ldc + col0 + hc + ch * 4;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z),
+                         "f"(t.w)
+                         : "memory");
+          }
+        }
+        __syncwarp();
+      } else if (row_ok) {
+        if (p.out_mode == 0) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + (size_t)row * p.ldc + col0 + hc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j * 8 < hcols) dst[j] = pack8(v + j * 8);
+        } else {   // out_mode 2: fp32 store
+          float* dst = reinterpret_cast<float*>(at.c_ptr ? at.c_ptr : p.C) + (size_t)row * p.ldc + col0 + hc;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j * 4 < hcols)
+              reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    }
+    if (to_tma) {
+      uint8_t* buf = my_store;
       fence_async_smem();
       __syncwarp();
       if (s_stats != nullptr) {
         // batch statistics of the following BatchNorm: column sums of the bf16 values just staged.  Lane l
         // owns columns 2l, 2l+1 of this 64-column chunk and walks the 32 staged rows (one conflict-free
-        // 4-byte shared load per row: the 16-byte unit is un-swizzled per row); partials go to the CTA's
-        // shared accumulators, which are flushed to global memory ONCE per CTA.  Rows past the end of the
-        // matrix were computed from zero-filled operands and contribute nothing.
+        // 4-byte shared load per row); partials go to the CTA's shared accumulators, flushed to global
+        // memory ONCE per CTA.  GEMM rows past M come from zero-filled operands and add nothing; rows of a
+        // convolution tile outside the image are masked (they see partly valid taps).
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
         const uint32_t base = smem_u32(buf) + (uint32_t)((lane & 3) << 2);
         uint32_t rows_ok = 0xffffffffu;
@@ -404,10 +448,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
           rows_ok = __ballot_sync(0xffffffffu, rw < at.vw && rh < at.vh && rn < at.vn);
         }
 #pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          if (!((rows_ok >> r) & 1u)) continue;
+        for (int rr = 0; rr < 32; ++rr) {
           uint32_t w;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + r * 128 + ((((lane >> 2) ^ (r & 7))) << 4)));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4)));
+          if (!((rows_ok >> rr) & 1u)) w = 0u;
           const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
           s0 += a; q0 = fmaf(a, a, q0);
           s1 += b; q1 = fmaf(b, b, q1);
@@ -429,49 +473,6 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
         }
         tma_store_commit();
       }
-    } else if (row_ok) {
-      if (p.out_mode == 0) {
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) +
-                                              (size_t)row * p.ldc + col0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j * 8 < ncols) dst[j] = pack8(v + j * 8);
-      } else {
-        float* dst = reinterpret_cast<float*>(at.c_ptr ? at.c_ptr : p.C) + (size_t)row * p.ldc + col0;
-        if (p.out_mode == 2) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j * 4 < ncols)
-              reinterpret_cast<float4*>(dst)[j] =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      }
-    }
-    if (p.out_mode == 1) {
-      // split-K accumulation: transpose the 32 x 64 fp32 slab through the (8 KB) staging buffer so that a
-      // warp-level RED covers two 256-byte row segments with 16-byte vectors (red.global.add.v4.f32)
-      // instead of 32 scattered 4-byte atomics per instruction.
-      float* stage = reinterpret_cast<float*>(my_store);
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        *reinterpret_cast<float4*>(stage + lane * 64 + ((j ^ (lane & 15)) << 2)) =
-            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      __syncwarp();
-      float* cbase = reinterpret_cast<float*>(at.c_ptr ? at.c_ptr : p.C);
-      const int ch = lane & 15;
-#pragma unroll 4
-      for (int it = 0; it < 16; ++it) {
-        const int rr = it * 2 + (lane >> 4);
-        const float4 t = *reinterpret_cast<const float4*>(stage + rr * 64 + ((ch ^ (rr & 15)) << 2));
-        if (m_row0 + rr < p.M && ch * 4 < ncols) {
-          float* dst = cbase + (size_t)(m_row0 + rr) * p.ldc + col0 + ch * 4;
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z),
-                       "f"(t.w)
-                       : "memory");
-        }
-      }
-      __syncwarp();
     }
   }
 }
