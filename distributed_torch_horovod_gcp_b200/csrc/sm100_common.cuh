@@ -309,8 +309,18 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
                       : make_uint4(0, 0, 0, 0);
       }
     }
-    if (to_tma || p.out_mode == 1) {
-      if (lane == 0) tma_store_wait_read<0>();       // the previous chunk's bulk stores have read the staging
+    // Staging: two 4 KB buffers per warp.  When the second one is not needed for the pre-activation tile or
+    // the residual transpose, consecutive chunks ALTERNATE between them and only wait for the store issued
+    // two chunks ago (cp.async.bulk.wait_group.read 1) — otherwise every chunk stalls on its predecessor's
+    // bulk store reading shared memory.
+    const bool dbuf = to_tma && !z_tma && !res_smem;
+    // buffer parity must alternate over the sequence of chunks THIS warp stages, across tiles: with an even
+    // number of chunks per tile the chunk index does it, with one chunk per tile the (alternating) accumulator
+    // index does
+    const int par = (((c0 - c_begin) >> 6) + acc * (((c_end - c_begin) >> 6) & 1)) & 1;
+    uint8_t* out_buf = my_store + ((dbuf && par) ? 4096 : 0);
+    if (res_smem) {
+      if (lane == 0) tma_store_wait_read<0>();       // (second buffer is about to be rewritten)
       __syncwarp();
     }
     if (res_smem) {
@@ -346,6 +356,10 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
         }
         if (p.preact != nullptr) {
           if (z_tma) {            // pre-activation tile -> second staging buffer (stored by TMA with the output)
+            if (half == 0) {
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(my_store + 4096 + lane * 128 + (((half * 4 + j) ^ (lane & 7)) << 4)) =
@@ -387,10 +401,17 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
         }
       }
       if (to_tma) {
+        if (half == 0) {       // the bulk store that last read this buffer must be done reading it
+          if (lane == 0) {
+            if (dbuf) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
+          __syncwarp();
+        }
         // this half of the 32 x 128 B swizzled staging rows (conflict-free 16-byte stores)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(my_store + lane * 128 + (((half * 4 + j) ^ (lane & 7)) << 4)) = pack8(v + j * 8);
+          *reinterpret_cast<uint4*>(out_buf + lane * 128 + (((half * 4 + j) ^ (lane & 7)) << 4)) = pack8(v + j * 8);
       } else if (p.out_mode == 1) {
         // split-K accumulation: transpose the 32 x 32 fp32 half through the staging buffer so that a
         // warp-level RED covers four 128-byte row segments with 16-byte vectors (red.global.add.v4.f32)
@@ -431,7 +452,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
       }
     }
     if (to_tma) {
-      uint8_t* buf = my_store;
+      uint8_t* buf = out_buf;
       fence_async_smem();
       __syncwarp();
       if (s_stats != nullptr) {
