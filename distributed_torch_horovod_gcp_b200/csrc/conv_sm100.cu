@@ -245,7 +245,13 @@ conv_bf16_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     const int c_begin = (BN >= 128) ? half * (BN / 2) : 0;
     const int c_end = (BN >= 128) ? c_begin + BN / 2 : (half == 0 ? BN : 0);
     uint8_t* my_store = smem_store + (warp - 2) * (2 * 4096);
+    float* my_stats = s_stats + (warp - 2) * STATS_WARP_FLOATS;
+    int stats_n = -1;
     for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+      if (want_stats && (w % nnb) != stats_n) {
+        if (stats_n >= 0) stats_flush<BN>(p.g, s_stats, stats_n * BN, (warp - 2) * 32 + lane);
+        stats_n = w % nnb;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (MODE != MODE_WGRAD) {
@@ -264,7 +270,7 @@ conv_bf16_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
         at.sh = (32 / at.sw) < p.bh ? (32 / at.sw) : p.bh;
         at.vw = p.out_w - at.w; at.vh = p.out_h - at.h; at.vn = p.out_n - at.n;
         epilogue_rows<BN>(p.g, &maps.out[cl.out_map], nullptr, tmem_base, acc, q, lane, 0, nt * BN, c_begin,
-                          c_end, my_store, at, want_stats ? s_stats : nullptr);
+                          c_end, my_store, at, want_stats ? my_stats : nullptr);
       } else {
         const int tile = w % tiles;
         const ConvTap tap = p.cls[0].taps[tile % p.num_taps_total];
@@ -281,7 +287,7 @@ conv_bf16_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (want_stats) stats_flush(p.g, s_stats, (warp - 2) * 32 + lane);
+    if (want_stats && stats_n >= 0) stats_flush<BN>(p.g, s_stats, stats_n * BN, (warp - 2) * 32 + lane);
     if (MODE != MODE_WGRAD && lane == 0) tma_store_wait_all();
   }
 
@@ -313,8 +319,8 @@ constexpr int HALO_A_STAGES = 3;
 template <int BN>
 struct HaloCfg {
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
-  static constexpr int B_STAGES = (BN == 256) ? 3 : ((BN == 128) ? 6 : 8);
-  static constexpr int STORE_BYTES = EPI_WARPS * 4096;
+  static constexpr int B_STAGES = (BN == 256) ? 2 : ((BN == 128) ? 5 : 8);
+  static constexpr int STORE_BYTES = EPI_WARPS * 2 * 4096;   // two staging buffers per epilogue warp
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int SMEM_BYTES = HALO_A_STAGES * HALO_A_BYTES + B_STAGES * B_BYTES + STORE_BYTES + 1024 + 256 +
                                     STATS_SMEM_BYTES;
@@ -475,8 +481,14 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
     const int half = (warp - 2) >> 2;
     const int c_begin = (BN >= 128) ? half * (BN / 2) : 0;
     const int c_end = (BN >= 128) ? c_begin + BN / 2 : (half == 0 ? BN : 0);
-    uint8_t* my_store = smem_store + (warp - 2) * 4096;
+    uint8_t* my_store = smem_store + (warp - 2) * (2 * 4096);
+    float* my_stats = s_stats + (warp - 2) * STATS_WARP_FLOATS;
+    int stats_n = -1;
     for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
+      if (want_stats && (w % nnb) != stats_n) {
+        if (stats_n >= 0) stats_flush<BN>(p.g, s_stats, stats_n * BN, (warp - 2) * 32 + lane);
+        stats_n = w % nnb;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const int nt = w % nnb;
@@ -492,13 +504,13 @@ conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ 
       at.sw = HALO_BW; at.sh = 4;
       at.vw = p.out_w - at.w; at.vh = p.out_h - at.h; at.vn = p.out_n - at.n;
       epilogue_rows<BN>(p.g, &maps.out[cl.out_map], nullptr, tmem_base, acc, q, lane, 0, nt * BN, c_begin, c_end,
-                        my_store, at, want_stats ? s_stats : nullptr);
+                        my_store, at, want_stats ? my_stats : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (want_stats) stats_flush(p.g, s_stats, (warp - 2) * 32 + lane);
+    if (want_stats && stats_n >= 0) stats_flush<BN>(p.g, s_stats, stats_n * BN, (warp - 2) * 32 + lane);
     if (lane == 0) tma_store_wait_all();
   }
 

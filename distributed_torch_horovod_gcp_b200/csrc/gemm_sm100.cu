@@ -168,20 +168,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int c_begin = (BN >= 128) ? half * (BN / 2) : 0;
     const int c_end = (BN >= 128) ? c_begin + BN / 2 : (half == 0 ? BN : 0);
     uint8_t* my_store = smem_store + (warp - 2) * (2 * 4096);
+    float* my_stats = s_stats + (warp - 2) * STATS_WARP_FLOATS;
+    int stats_n = -1;                             // column block the shared statistics belong to
     for (int w = blockIdx.x; w < work_items; w += gridDim.x) {
       const int tile = w % tiles;
       const int m_idx = (p.n_fastest ? tile / p.num_n_blocks : tile % p.num_m_blocks) * BLOCK_M;
       const int n_idx = (p.n_fastest ? tile % p.num_n_blocks : tile / p.num_m_blocks) * BN;
+      if (want_stats && n_idx != stats_n) {
+        if (stats_n >= 0) stats_flush<BN>(p, s_stats, stats_n, (warp - 2) * 32 + lane);
+        stats_n = n_idx;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epilogue_rows<BN>(p, &map_c, &map_z, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, c_begin, c_end,
-                        my_store, StoreAt{0, 0, 0, 0, nullptr}, want_stats ? s_stats : nullptr);
+                        my_store, StoreAt{0, 0, 0, 0, nullptr}, want_stats ? my_stats : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (want_stats) stats_flush(p, s_stats, (warp - 2) * 32 + lane);
+    if (want_stats && stats_n >= 0) stats_flush<BN>(p, s_stats, stats_n, (warp - 2) * 32 + lane);
     if (p.tma_store && lane == 0) tma_store_wait_all();   // smem must outlive the bulk reads
   }
 
@@ -409,21 +415,27 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int half = (warp - 2) >> 2;
     const int c_begin = half * (BN2 / 2), c_end = c_begin + BN2 / 2;
     uint8_t* my_store = smem_store + (warp - 2) * (2 * 4096);
+    float* my_stats = s_stats + (warp - 2) * STATS_WARP_FLOATS;
+    int stats_n = -1;
     for (int w = cluster_id; w < work_items; w += num_clusters) {
       const int tile = w % tiles;
       const int m_idx = (p.n_fastest ? tile / p.num_n_blocks : tile % num_m2) * (2 * BLOCK_M) +
                         (int)cta_rank * BLOCK_M;
       const int n_idx = (p.n_fastest ? tile % p.num_n_blocks : tile / num_m2) * BN2;
+      if (want_stats && n_idx != stats_n) {
+        if (stats_n >= 0) stats_flush<BN2>(p, s_stats, stats_n, (warp - 2) * 32 + lane);
+        stats_n = n_idx;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epilogue_rows<BN2>(p, &map_c, &map_z, tmem_base, acc, q, lane, m_idx + q * 32, n_idx, c_begin, c_end,
-                         my_store, StoreAt{0, 0, 0, 0, nullptr}, want_stats ? s_stats : nullptr);
+                         my_store, StoreAt{0, 0, 0, 0, nullptr}, want_stats ? my_stats : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(leader_addr(&tmem_empty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (want_stats) stats_flush(p, s_stats, (warp - 2) * 32 + lane);
+    if (want_stats && stats_n >= 0) stats_flush<BN2>(p, s_stats, stats_n, (warp - 2) * 32 + lane);
     if (p.tma_store && lane == 0) tma_store_wait_all();
   }
 

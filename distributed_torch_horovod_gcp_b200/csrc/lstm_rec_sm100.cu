@@ -720,7 +720,7 @@ int launch_cluster(K kern, const P& p, int clusters, int smem_bytes, cudaStream_
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return lfail(cudaGetErrorString(e), (int)e);
   cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
+  cfg = cudaLaunchConfig_t{};
   cfg.gridDim = dim3(CL * clusters);
   cfg.blockDim = dim3(LTHREADS);
   cfg.dynamicSmemBytes = smem_bytes;

@@ -35,9 +35,13 @@ struct GemmParams {
                            // statistics of the BatchNorm that follows), accumulated by the epilogue
 };
 
-// Per-CTA shared-memory accumulators for GemmParams::stats: 2 * STATS_MAX_N floats after the barriers.
+// Shared-memory accumulators for GemmParams::stats, after the barriers: one PRIVATE region per epilogue warp
+// (sum[128] | sumsq[128] floats for the <= 128 tile columns the warp drains).  Every address is only ever
+// touched by one lane, so accumulation is plain ld/add/st — fp32 atomicAdd on shared memory compiles to a
+// CAS loop (ATOMS.CAST.SPIN) and the four lane-quarter warps of a tile hit the same columns.
 constexpr int STATS_MAX_N = 2048;
-constexpr int STATS_SMEM_BYTES = 2 * STATS_MAX_N * 4;
+constexpr int STATS_WARP_FLOATS = 256;
+constexpr int STATS_SMEM_BYTES = 8 * STATS_WARP_FLOATS * 4;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -477,13 +481,12 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
           s0 += a; q0 = fmaf(a, a, q0);
           s1 += b; q1 = fmaf(b, b, q1);
         }
-        const int c = col0 + 2 * lane;
-        if (c < p.N) {        // N % 8 == 0: the pair is in or out together
-          atomicAdd(s_stats + c, s0);
-          atomicAdd(s_stats + c + 1, s1);
-          atomicAdd(s_stats + STATS_MAX_N + c, q0);
-          atomicAdd(s_stats + STATS_MAX_N + c + 1, q1);
-        }
+        // lane-private slots of the warp's region (columns past N hold zeros: zero-filled B rows)
+        float2* ps = reinterpret_cast<float2*>(s_stats + (c0 - c_begin) + 2 * lane);
+        float2* pq = reinterpret_cast<float2*>(s_stats + (STATS_WARP_FLOATS / 2) + (c0 - c_begin) + 2 * lane);
+        float2 vs = *ps, vq = *pq;
+        vs.x += s0; vs.y += s1; vq.x += q0; vq.y += q1;
+        *ps = vs; *pq = vq;
       }
       if (lane == 0) {
         if (at.rank4) {
@@ -499,16 +502,34 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
 }
 
 // shared accumulators of GemmParams::stats: zero (all threads, before the kernel's first __syncthreads) and
-// flush (the 8 epilogue warps, after their tile loop: named barrier 2 among the 256 of them)
+// flush (all 8 epilogue warps together — named barrier 2 among the 256 of them — whenever the CTA moves to
+// another column block and after its last tile): the four lane-quarter regions of a column are summed and
+// added to global memory once.
 __device__ __forceinline__ void stats_zero(float* s_stats, int nthreads) {
-  for (int i = threadIdx.x; i < 2 * STATS_MAX_N; i += nthreads) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * STATS_WARP_FLOATS; i += nthreads) s_stats[i] = 0.f;
 }
-__device__ __forceinline__ void stats_flush(const GemmParams& p, const float* s_stats, int epi_tid) {
+template <int BN>
+__device__ __forceinline__ void stats_flush(const GemmParams& p, float* s_stats, int n_idx, int epi_tid) {
+  constexpr int HALF = (BN >= 128) ? BN / 2 : BN;         // columns per epilogue warp
   asm volatile("bar.sync 2, 256;" ::: "memory");
-  for (int c = epi_tid; c < p.N; c += EPI_WARPS * 32) {
-    atomicAdd(p.stats + c, s_stats[c]);
-    atomicAdd(p.stats + p.N + c, s_stats[STATS_MAX_N + c]);
+  if (epi_tid < BN) {
+    const int h = epi_tid / HALF, l = epi_tid % HALF;
+    const float* r = s_stats + (h * 4) * STATS_WARP_FLOATS + l;
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s += r[k * STATS_WARP_FLOATS];
+      q += r[k * STATS_WARP_FLOATS + STATS_WARP_FLOATS / 2];
+    }
+    if (n_idx + epi_tid < p.N) {
+      atomicAdd(p.stats + n_idx + epi_tid, s);
+      atomicAdd(p.stats + p.N + n_idx + epi_tid, q);
+    }
   }
+  asm volatile("bar.sync 2, 256;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_stats[i * 256 + epi_tid] = 0.f;
+  asm volatile("bar.sync 2, 256;" ::: "memory");
 }
 
 // cuTensorMapEncode* is a driver-API call: it fails with CUDA_ERROR_INVALID_CONTEXT on a thread that
