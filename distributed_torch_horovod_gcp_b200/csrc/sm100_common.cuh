@@ -279,6 +279,25 @@ struct StoreAt {
   int sw, sh, vw, vh, vn;
 };
 
+// explicit shared-space accesses (a generic pointer into shared memory costs 64-bit address arithmetic
+// and the generic LD/ST path: measured, the epilogue is issue-bound)
+__device__ __forceinline__ void epi_sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 epi_lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 pack8r(const uint32_t* r) {   // 8 fp32 bit patterns -> 8 bf16
+  uint4 o;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(__uint_as_float(r[1])), "f"(__uint_as_float(r[0])));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(__uint_as_float(r[3])), "f"(__uint_as_float(r[2])));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(__uint_as_float(r[5])), "f"(__uint_as_float(r[4])));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(__uint_as_float(r[7])), "f"(__uint_as_float(r[6])));
+  return o;
+}
+
 template <int BN>
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtensorMap* map_c,
                                               const CUtensorMap* map_z, uint32_t tmem_base, int acc, int q,
@@ -294,6 +313,12 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
   const bool to_tma = p.out_mode == 0 && p.tma_store;
   const bool z_tma = p.preact != nullptr && to_tma;
   const bool res_smem = p.residual != nullptr && p.preact == nullptr && p.out_mode != 1;
+  // the common case (plain bf16 output, optionally with BN statistics): no per-element work at all
+  const bool plain = to_tma && p.alpha == 1.0f && p.bias == nullptr && p.bias_f32 == nullptr &&
+                     p.preact == nullptr && p.act == 0 && p.residual == nullptr;
+  const uint32_t store_s = smem_u32(my_store);
+  const uint32_t lane_row = (uint32_t)lane * 128u;
+  const uint32_t lsw = (uint32_t)(lane & 7);
 #pragma unroll 1
   for (int c0 = c_begin; c0 < c_end; c0 += 64) {
     const int col0 = n_idx + c0;
@@ -322,30 +347,52 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
     // number of chunks per tile the chunk index does it, with one chunk per tile the (alternating) accumulator
     // index does
     const int par = (((c0 - c_begin) >> 6) + acc * (((c_end - c_begin) >> 6) & 1)) & 1;
-    uint8_t* out_buf = my_store + ((dbuf && par) ? 4096 : 0);
+    const uint32_t out_s = store_s + ((dbuf && par) ? 4096u : 0u);
     if (res_smem) {
       if (lane == 0) tma_store_wait_read<0>();       // (second buffer is about to be rewritten)
       __syncwarp();
-    }
-    if (res_smem) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = i * 4 + (lane >> 3), u = lane & 7;
-        *reinterpret_cast<uint4*>(my_store + 4096 + rr * 128 + ((u ^ (rr & 7)) << 4)) = resv[i];
+        epi_sts128(store_s + 4096u + rr * 128 + ((u ^ (rr & 7)) << 4), resv[i]);
       }
       __syncwarp();
     }
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0);
+    if (plain) {
+      // ---- fast path: TMEM -> bf16 -> swizzled staging rows, nothing else ----
+      uint32_t r[32];
+      tc_ld_32x32b_x32(taddr, r);
+      if (lane == 0) {       // the bulk store that last read this buffer must be done reading it
+        if (dbuf) tma_store_wait_read<1>();
+        else tma_store_wait_read<0>();
+      }
+      tc_wait_ld();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) epi_sts128(out_s + lane_row + ((j ^ lsw) << 4), pack8r(r + j * 8));
+      if (ncols > 32) {
+        tc_ld_32x32b_x32(taddr + 32, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) epi_sts128(out_s + lane_row + (((4 + j) ^ lsw) << 4), pack8r(r + j * 8));
+      }
+    } else {
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
       const int hc = half * 32;                      // first column of this half inside the chunk
       if (hc >= ncols) break;                        // warp-uniform
       const int hcols = min(32, ncols - hc);
       uint32_t r[32];
-      tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0 + hc), r);
+      tc_ld_32x32b_x32(taddr + hc, r);
       tc_wait_ld();
       float v[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      if (p.alpha != 1.0f) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+      }
       if (p.out_mode != 1) {
         if (p.bias != nullptr) {
           const __nv_bfloat16* b = reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0 + hc;
@@ -366,8 +413,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(my_store + 4096 + lane * 128 + (((half * 4 + j) ^ (lane & 7)) << 4)) =
-                  pack8(v + j * 8);
+              epi_sts128(store_s + 4096u + lane_row + (((half * 4 + j) ^ lsw) << 4), pack8(v + j * 8));
           } else if (row_ok) {
             uint4* pp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.preact) +
                                                  (size_t)row * p.ldc + col0 + hc);
@@ -390,10 +436,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
           for (int j = 0; j < 4; ++j) {
             if (j * 8 < hcols) {
               float a[8];
-              unpack8(res_smem ? *reinterpret_cast<const uint4*>(my_store + 4096 + lane * 128 +
-                                                                 (((half * 4 + j) ^ (lane & 7)) << 4))
-                               : rp[j],
-                      a);
+              unpack8(res_smem ? epi_lds128(store_s + 4096u + lane_row + (((half * 4 + j) ^ lsw) << 4)) : rp[j], a);
 #pragma unroll
               for (int t = 0; t < 8; ++t) {
                 if (p.act == 3) v[j * 8 + t] *= gelu_erf_grad(a[t]);
@@ -415,27 +458,27 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
         // this half of the 32 x 128 B swizzled staging rows (conflict-free 16-byte stores)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(out_buf + lane * 128 + (((half * 4 + j) ^ (lane & 7)) << 4)) = pack8(v + j * 8);
+          epi_sts128(out_s + lane_row + (((half * 4 + j) ^ lsw) << 4), pack8(v + j * 8));
       } else if (p.out_mode == 1) {
         // split-K accumulation: transpose the 32 x 32 fp32 half through the staging buffer so that a
         // warp-level RED covers four 128-byte row segments with 16-byte vectors (red.global.add.v4.f32)
-        float* stage = reinterpret_cast<float*>(my_store);
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-              make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          epi_sts128(store_s + lane_row + ((j ^ lsw) << 4),
+                 make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                            __float_as_uint(v[4 * j + 3])));
         __syncwarp();
         float* cbase = reinterpret_cast<float*>(at.c_ptr ? at.c_ptr : p.C);
         const int ch = lane & 7;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int rr = it * 4 + (lane >> 3);
-          const float4 t = *reinterpret_cast<const float4*>(stage + rr * 32 + ((ch ^ (rr & 7)) << 2));
+          const uint4 t = epi_lds128(store_s + rr * 128 + ((ch ^ (rr & 7)) << 4));
           if (m_row0 + rr < p.M && ch * 4 < hcols) {
             float* dst = cbase + (size_t)(m_row0 + rr) * p.ldc + col0 + hc + ch * 4;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(t.x), "f"(t.y), "f"(t.z),
-                         "f"(t.w)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(t.x), "r"(t.y), "r"(t.z),
+                         "r"(t.w)
                          : "memory");
           }
         }
@@ -455,40 +498,55 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
         }
       }
     }
+    }
     if (to_tma) {
-      uint8_t* buf = out_buf;
       fence_async_smem();
       __syncwarp();
       if (s_stats != nullptr) {
         // batch statistics of the following BatchNorm: column sums of the bf16 values just staged.  Lane l
         // owns columns 2l, 2l+1 of this 64-column chunk and walks the 32 staged rows (one conflict-free
-        // 4-byte shared load per row); partials go to the CTA's shared accumulators, flushed to global
-        // memory ONCE per CTA.  GEMM rows past M come from zero-filled operands and add nothing; rows of a
+        // 4-byte shared load per row, packed fp32x2 add / fma); partials go to the warp's private shared
+        // accumulators.  GEMM rows past M come from zero-filled operands and add nothing; rows of a
         // convolution tile outside the image are masked (they see partly valid taps).
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        const uint32_t base = smem_u32(buf) + (uint32_t)((lane & 3) << 2);
-        uint32_t rows_ok = 0xffffffffu;
+        unsigned long long sum2 = 0ull, sq2 = 0ull;
+        const uint32_t base = out_s + (uint32_t)((lane & 3) << 2);
+        const uint32_t u = (uint32_t)(lane >> 2);
         if (at.rank4) {      // lane r decides for slab row r
           const int rw = lane % at.sw, rh = (lane / at.sw) % at.sh, rn = lane / (at.sw * at.sh);
-          rows_ok = __ballot_sync(0xffffffffu, rw < at.vw && rh < at.vh && rn < at.vn);
-        }
+          const uint32_t rows_ok = __ballot_sync(0xffffffffu, rw < at.vw && rh < at.vh && rn < at.vn);
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          uint32_t w;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4)));
-          if (!((rows_ok >> rr) & 1u)) w = 0u;
-          const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
-          s0 += a; q0 = fmaf(a, a, q0);
-          s1 += b; q1 = fmaf(b, b, q1);
+          for (int rr = 0; rr < 32; ++rr) {
+            uint32_t w;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + rr * 128 + ((u ^ (rr & 7)) << 4)));
+            if (!((rows_ok >> rr) & 1u)) w = 0u;
+            unsigned long long ab;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(ab) : "r"(w << 16), "r"(w & 0xffff0000u));
+            asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sum2) : "l"(ab));
+            asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(sq2) : "l"(ab));
+          }
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            uint32_t w;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + rr * 128 + ((u ^ (rr & 7)) << 4)));
+            unsigned long long ab;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(ab) : "r"(w << 16), "r"(w & 0xffff0000u));
+            asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sum2) : "l"(ab));
+            asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(sq2) : "l"(ab));
+          }
         }
         // lane-private slots of the warp's region (columns past N hold zeros: zero-filled B rows)
-        float2* ps = reinterpret_cast<float2*>(s_stats + (c0 - c_begin) + 2 * lane);
-        float2* pq = reinterpret_cast<float2*>(s_stats + (STATS_WARP_FLOATS / 2) + (c0 - c_begin) + 2 * lane);
-        float2 vs = *ps, vq = *pq;
-        vs.x += s0; vs.y += s1; vq.x += q0; vq.y += q1;
-        *ps = vs; *pq = vq;
+        const uint32_t ps = smem_u32(s_stats) + (uint32_t)(((c0 - c_begin) + 2 * lane) << 2);
+        unsigned long long a0, a1;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(a0) : "r"(ps));
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(a1) : "r"(ps + (STATS_WARP_FLOATS / 2) * 4));
+        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a0) : "l"(sum2));
+        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a1) : "l"(sq2));
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(ps), "l"(a0) : "memory");
+        asm volatile("st.shared.b64 [%0], %1;" ::"r"(ps + (STATS_WARP_FLOATS / 2) * 4), "l"(a1) : "memory");
       }
       if (lane == 0) {
+        const uint8_t* buf = my_store + (out_s - store_s);
         if (at.rank4) {
           tma_store_4d(map_c, buf, col0, at.w, at.h, at.n);
         } else {

@@ -173,13 +173,13 @@ def _is_gemm_conv(x, conv) -> bool:
 
 
 _USE_STEM_GEMM = os.environ.get("B200DP_STEM_GEMM", "1") == "1"
-STEM_KP = 152
+STEM_KP = 168          # k = kh*24 + kw*3 + c (21 real + 3 zero-weighted columns per kernel row)
 
 
 class _StemConvFn(torch.autograd.Function):
     """ResNet stem (7x7, stride 2, pad 3, 3 input channels) as im2col + tcgen05 GEMM.  cuDNN runs
     this layer on legacy sm80 kernels (1.5 ms fwd + 0.8 ms wgrad at batch 256); the im2col matrix
-    ([N*112*112, 152] bf16) is kept for the weight gradient — HBM capacity is not the constraint
+    ([N*112*112, 168] bf16) is kept for the weight gradient — HBM capacity is not the constraint
     on a 180 GB part, bandwidth is."""
 
     @staticmethod
@@ -192,8 +192,9 @@ class _StemConvFn(torch.autograd.Function):
                                     torch.cuda.current_stream(x.device).cuda_stream))
         counters.bump("stem_im2col")
         Cout = weight.shape[0]
-        wp = torch.zeros((Cout, STEM_KP), dtype=torch.bfloat16, device=x.device)
-        wp[:, :147] = weight.permute(0, 2, 3, 1).reshape(Cout, 147)      # [Cout][kh][kw][c]
+        wp = torch.zeros((Cout, 7, 24), dtype=torch.bfloat16, device=x.device)
+        wp[:, :, :21] = weight.permute(0, 2, 3, 1).reshape(Cout, 7, 21)  # [Cout][kh][kw*3 + c]
+        wp = wp.view(Cout, STEM_KP)
         y = torch.empty((M, Cout), dtype=torch.bfloat16, device=x.device)
         _gemm.gemm(cols, wp, y, M, Cout, STEM_KP, stats=stats)
         ctx.save_for_backward(cols)
@@ -211,7 +212,7 @@ class _StemConvFn(torch.autograd.Function):
         acc = torch.zeros((Cout, STEM_KP), dtype=torch.float32, device=dy.device)
         _gemm.gemm(dy2, cols, acc, Cout, STEM_KP, M, a_mn=True, b_mn=True, out_mode=1,
                    splits=_gemm._splits_for(Cout, STEM_KP, M))
-        dw = acc[:, :147].reshape(Cout, 7, 7, 3).permute(0, 3, 1, 2).to(torch.bfloat16)
+        dw = acc.view(Cout, 7, 24)[:, :, :21].reshape(Cout, 7, 7, 3).permute(0, 3, 1, 2).to(torch.bfloat16)
         return None, dw.contiguous(memory_format=torch.channels_last), None
 
 
