@@ -163,6 +163,14 @@ def shutdown() -> None:
             except Exception:
                 pass
             rt.symm = None
+            # physical memory of a symmetric allocation is returned when the LAST handle to it goes — the
+            # peers' imported handles included: wait until every rank has closed before reporting done
+            try:
+                if rt.cpu_group is not None and dist.is_initialized() and rt.size > 1:
+                    import datetime
+                    dist.monitored_barrier(group=rt.cpu_group, timeout=datetime.timedelta(seconds=10))
+            except Exception:      # a dead peer must not block teardown
+                pass
         if rt.owns_pg and dist.is_initialized():
             try:
                 dist.destroy_process_group()

@@ -566,6 +566,43 @@ __global__ void __launch_bounds__(THREADS) stem_im2col_kernel(const __nv_bfloat1
   }
 }
 
+
+// ---- global average pool over the HW positions of an NHWC bf16 tensor ------------------------------------
+// forward: y[n][c] = mean_hw x[n][hw][c]; backward: dx[n][hw][c] = dy[n][c] / HW (ATen's expand + mul + layout
+// copy for the same thing are 2 kernels / 120 us at [256, 2048, 7, 7]; this is one 51 MB write).
+__global__ void __launch_bounds__(THREADS) avgpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                              int HW, int V, long long total, float inv) {
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * THREADS) {
+    const long long n = i / V;
+    const int v = (int)(i % V);
+    const uint4* src = x + n * HW * V + v;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int h = 0; h < HW; ++h) {
+      float f[8];
+      unpack8(src[(long long)h * V], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    y[i] = pack8(acc);
+  }
+}
+__global__ void __launch_bounds__(THREADS) avgpool_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx,
+                                                              int HW, int V, long long total, float inv) {
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * THREADS) {
+    const long long n = i / ((long long)HW * V);
+    const int v = (int)(i % V);
+    float f[8];
+    unpack8(dy[n * V + v], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= inv;
+    dx[i] = pack8(f);
+  }
+}
+
 thread_local char g_err[256];
 int fail(const char* what, cudaError_t e) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -810,6 +847,33 @@ int b200dp_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, 
                                                                              (uint4*)dx, N, H, W, OH, OW, V);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("maxpool_bwd launch", e);
+  return 0;
+}
+
+// x: NHWC bf16 [N, HW, C] -> y [N, C] (C % 8 == 0)
+int b200dp_avgpool_fwd(const void* x, void* y, long long N, int HW, int C, unsigned long long stream) {
+  if (C % 8) return -1;
+  const int V = C / 8;
+  const long long total = N * V;
+  int grid = (int)((total + THREADS - 1) / THREADS);
+  if (grid > reduce_grid() * 8) grid = reduce_grid() * 8;
+  avgpool_fwd_kernel<<<grid, THREADS, 0, (cudaStream_t)(uintptr_t)stream>>>((const uint4*)x, (uint4*)y, HW, V, total,
+                                                                             1.0f / (float)HW);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("avgpool_fwd launch", e);
+  return 0;
+}
+
+int b200dp_avgpool_bwd(const void* dy, void* dx, long long N, int HW, int C, unsigned long long stream) {
+  if (C % 8) return -1;
+  const int V = C / 8;
+  const long long total = N * HW * V;
+  int grid = (int)((total + THREADS - 1) / THREADS);
+  if (grid > reduce_grid() * 8) grid = reduce_grid() * 8;
+  avgpool_bwd_kernel<<<grid, THREADS, 0, (cudaStream_t)(uintptr_t)stream>>>((const uint4*)dy, (uint4*)dx, HW, V, total,
+                                                                             1.0f / (float)HW);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("avgpool_bwd launch", e);
   return 0;
 }
 

@@ -556,7 +556,7 @@ const char* b200dp_gemm_last_error() { return g_err; }
 int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                      int a_mn, int b_mn, const void* bias_bf16, const void* bias_f32, const void* residual,
                      void* preact, int act, int out_mode, float alpha, int splits, int block_n, int max_ctas,
-                     int two_cta, float* stats, unsigned long long stream) {
+                     int two_cta, float* stats, const void* res_mask, unsigned long long stream) {
   if (ensure_init()) return -1;
   if (M <= 0 || N <= 0 || K <= 0) return fail("bad shape");
   if ((N % 8) || (lda % 8) || (ldb % 8) || (ldc % 4) || ((out_mode == 0) && (ldc % 8)))
@@ -580,6 +580,10 @@ int b200dp_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K,
   p.act = act; p.out_mode = out_mode; p.C = C; p.bias = bias_bf16; p.bias_f32 = bias_f32;
   p.residual = residual; p.preact = preact; p.alpha = alpha;
   p.stats = stats;
+  p.res_mask = reinterpret_cast<const unsigned char*>(res_mask);
+  if (res_mask != nullptr && (residual == nullptr || preact != nullptr || act > 2 || out_mode != 0 || (N % 64) ||
+                              ldc != N))
+    return fail("res_mask: plain bf16 residual, dense rows and N % 64 == 0 required");
   if (stats != nullptr && (N > STATS_MAX_N || out_mode != 0)) return fail("stats: N <= 2048 and bf16 output required");
   p.tma_store = (out_mode == 0) ? 1 : 0;
   // B (N x K bf16) small enough to live in L2 next to the in-flight A tiles -> walk N first

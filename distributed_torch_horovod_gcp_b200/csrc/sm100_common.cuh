@@ -31,6 +31,9 @@ struct GemmParams {
   int n_fastest;           // tile order: consecutive CTAs walk the N blocks of one M block first (A tile is
                            // fetched from HBM once and re-used from L2 while the whole B matrix stays in L2)
   float alpha;
+  const unsigned char* res_mask;   // optional, with a plain residual (act 0..2): bit j of byte [row][col/8] keeps
+                           // residual element (row, 8*(col/8)+j) — the ReLU sign bits of the block output whose
+                           // skip-branch gradient the residual is (N % 64 == 0 required)
   float* stats;            // optional fp32 [2][N]: per-column sum | sum of squares of the bf16 OUTPUT (the batch
                            // statistics of the BatchNorm that follows), accumulated by the epilogue
 };
@@ -289,6 +292,12 @@ __device__ __forceinline__ uint4 epi_lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
+// prmt.b32 in its default mode: selector nibble bit 3 = replicate the selected byte's sign bit
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+  return d;
+}
 __device__ __forceinline__ uint4 pack8r(const uint32_t* r) {   // 8 fp32 bit patterns -> 8 bf16
   uint4 o;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(__uint_as_float(r[1])), "f"(__uint_as_float(r[0])));
@@ -316,6 +325,8 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
   // the common case (plain bf16 output, optionally with BN statistics): no per-element work at all
   const bool plain = to_tma && p.alpha == 1.0f && p.bias == nullptr && p.bias_f32 == nullptr &&
                      p.preact == nullptr && p.act == 0 && p.residual == nullptr;
+  const bool res_only = to_tma && res_smem && p.alpha == 1.0f && p.bias == nullptr && p.bias_f32 == nullptr &&
+                        p.act == 0;
   const uint32_t store_s = smem_u32(my_store);
   const uint32_t lane_row = (uint32_t)lane * 128u;
   const uint32_t lsw = (uint32_t)(lane & 7);
@@ -336,6 +347,28 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
         resv[i] = (m_row0 + rr < p.M && u * 8 < ncols)
                       ? *reinterpret_cast<const uint4*>(rbase + (size_t)(m_row0 + rr) * p.ldc + col0 + u * 8)
                       : make_uint4(0, 0, 0, 0);
+      }
+      if (p.res_mask != nullptr) {
+        // ReLU sign bits of the residual (1 byte per 8 channels): bit j -> 16-bit lane j.  Byte k of
+        // ((bits * 0x01010101) & 0x08040201) + 0x7f7f7f7f has its MSB set iff bit k is, and PRMT's
+        // sign-replicate mode turns that MSB into 0x00 / 0xff bytes.
+        uint32_t mbits[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + (lane >> 3), u = lane & 7;
+          mbits[i] = (m_row0 + rr < p.M && u * 8 < ncols)
+                         ? (uint32_t)p.res_mask[(size_t)(m_row0 + rr) * (size_t)(p.N >> 3) + (size_t)((col0 >> 3) + u)]
+                         : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t rep = mbits[i] * 0x01010101u;
+          const uint32_t lo = (rep & 0x08040201u) + 0x7f7f7f7fu, hi = (rep & 0x80402010u) + 0x7f7f7f7fu;
+          resv[i].x &= prmt_sign(lo, 0x9988u);
+          resv[i].y &= prmt_sign(lo, 0xbbaau);
+          resv[i].z &= prmt_sign(hi, 0x9988u);
+          resv[i].w &= prmt_sign(hi, 0xbbaau);
+        }
       }
     }
     // Staging: two 4 KB buffers per warp.  When the second one is not needed for the pre-activation tile or
@@ -376,6 +409,34 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, const CUtenso
         tc_wait_ld();
 #pragma unroll
         for (int j = 0; j < 4; ++j) epi_sts128(out_s + lane_row + (((4 + j) ^ lsw) << 4), pack8r(r + j * 8));
+      }
+    } else if (res_only) {
+      // ---- skip-gradient path of the dgrad GEMMs: bf16(acc + residual), packed fp32x2 adds ----
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        if (half * 32 >= ncols) break;
+        uint32_t r[32];
+        tc_ld_32x32b_x32(taddr + half * 32, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = lane_row + (((half * 4 + j) ^ lsw) << 4);
+          const uint4 rv = epi_lds128(store_s + 4096u + off);
+          const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+          uint4 o;
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            unsigned long long a2, b2;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "r"(r[j * 8 + 2 * w]), "r"(r[j * 8 + 2 * w + 1]));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(b2) : "r"(rw[w] << 16), "r"(rw[w] & 0xffff0000u));
+            asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a2) : "l"(b2));
+            uint32_t s0, s1;
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(s0), "=r"(s1) : "l"(a2));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(ow[w]) : "f"(__uint_as_float(s1)), "f"(__uint_as_float(s0)));
+          }
+          epi_sts128(out_s + off, o);      // the store that read this buffer was waited for above (res_smem)
+        }
       }
     } else {
 #pragma unroll 1

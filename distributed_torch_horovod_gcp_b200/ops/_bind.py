@@ -16,7 +16,7 @@ from .lstm_rec import lstm_recurrent  # noqa: F401
 from .conv import conv3x3, conv2d as conv2d_implicit  # noqa: F401
 from .ln import layer_norm  # noqa: F401
 from .gemm import linear, mlp, qkv_proj  # noqa: F401  (re-exported as kernels.linear / .mlp / .qkv_proj)
-from .bn import conv_bn_act, bn_act, max_pool_3x3_s2  # noqa: F401
+from .bn import conv_bn_act, bn_act, max_pool_3x3_s2, global_avg_pool  # noqa: F401
 
 
 def register(lib, have: Dict[str, bool]) -> None:

@@ -42,6 +42,10 @@ def register(lib, have):
     if hasattr(lib, "b200dp_stem_im2col"):
         lib.b200dp_stem_im2col.argtypes = [vp, vp, i, i, i, u64]
         have["stem_conv"] = True
+    if hasattr(lib, "b200dp_avgpool_fwd"):
+        lib.b200dp_avgpool_fwd.argtypes = [vp, vp, ctypes.c_longlong, i, i, u64]
+        lib.b200dp_avgpool_bwd.argtypes = [vp, vp, ctypes.c_longlong, i, i, u64]
+        have["global_avg_pool"] = True
     if hasattr(lib, "b200dp_maxpool_fwd"):
         lib.b200dp_maxpool_fwd.argtypes = [vp, vp, vp, i, i, i, i, u64]
         lib.b200dp_maxpool_bwd.argtypes = [vp, vp, vp, i, i, i, i, u64]
@@ -94,6 +98,8 @@ class _BNActFn(torch.autograd.Function):
         ctx.relu, ctx.has_res, ctx.pdtype = relu, residual is not None, gamma.dtype
         ctx.affine = (gamma, beta)
         ctx.box = box
+        if box is not None and residual is None and not relu and ctx.needs_input_grad[0]:
+            box.armed = box.want_mask = True      # consumer role (see backward)
         if ctx.needs_input_grad[1]:
             grad_sink.note_forward(gamma)
         if ctx.needs_input_grad[2]:
@@ -108,7 +114,17 @@ class _BNActFn(torch.autograd.Function):
         if not dy.is_contiguous(memory_format=torch.channels_last):
             dy = dy.contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x, memory_format=torch.channels_last)
-        dres = torch.empty_like(x, memory_format=torch.channels_last) if (ctx.has_res and ctx.relu) \
+        box = ctx.box
+        relu = ctx.relu
+        if box is not None and not ctx.has_res and not relu and box.ext_mask is not None:
+            # downsample BN of a projection block: ``dy`` is the block-output gradient BEFORE the block's
+            # final ReLU mask, whose sign bits the block's BN+add+ReLU backward left in the box
+            ext_mask, box.ext_mask = box.ext_mask, None
+            assert ext_mask.numel() == M * (C // 8)
+            mask, relu = ext_mask, True
+        # the masked skip gradient is only materialised when nobody downstream applies the sign bits itself
+        hand_off = ctx.has_res and ctx.relu and box is not None and box.armed and not box.consumed
+        dres = torch.empty_like(x, memory_format=torch.channels_last) if (ctx.has_res and ctx.relu and not hand_off) \
             else None
         sums = torch.empty(2 * C, dtype=torch.float32, device=x.device)
         # dgamma / dbeta: straight into the gradient-bucket slots when both parameters offer a sink
@@ -126,7 +142,7 @@ class _BNActFn(torch.autograd.Function):
                                dx.data_ptr(), dres.data_ptr() if dres is not None else None,
                                a.data_ptr(), mean.data_ptr(), invstd.data_ptr(), sums.data_ptr(),
                                dg_ptr, db_ptr,
-                               int(ctx.pdtype == torch.bfloat16), M, C, int(ctx.relu), st))
+                               int(ctx.pdtype == torch.bfloat16), M, C, int(relu), st))
         counters.bump("bn_bwd", 2)
         if direct:
             dgamma = dbeta = None
@@ -134,11 +150,17 @@ class _BNActFn(torch.autograd.Function):
             bdone()
         else:
             dgamma, dbeta = dgb[:C], dgb[C:]              # written by the kernel in the param dtype
-        if ctx.has_res and dres is None:
+        if hand_off:
+            if box.want_mask:
+                box.ext_mask = mask         # projection block: the downsample BN backward masks dy itself
+                dres = dy
+            else:
+                box.park(dy, mask)          # identity block: conv1's dgrad epilogue adds mask(dy)
+                dres = None
+        elif ctx.has_res and dres is None:
             dres = dy                       # no ReLU: the residual branch gets dy unchanged
-        if ctx.has_res and ctx.box is not None and ctx.box.armed:
-            ctx.box.dres = dres             # picked up by the block's first conv (dgrad epilogue adds it)
-            dres = None
+            if box is not None and not box.want_mask and box.park(dres):
+                dres = None
         return dx, dgamma, dbeta, None, None, dres, None, None, None, None, None, None
 
 
@@ -227,7 +249,7 @@ def _is_stem_conv(x, conv) -> bool:
 _FUSE_STATS = os.environ.get("B200DP_BN_STATS_IN_EPILOGUE", "1") == "1"
 
 
-def conv2d(x, conv: torch.nn.Conv2d, box=None, stats=None):
+def conv2d(x, conv: torch.nn.Conv2d, box=None, stats=None, park=None):
     """Convolution of an NHWC bf16 activation; 1x1/stride-1 and the 7x7 stem -> tcgen05 GEMM, 3x3 and
     strided 1x1 -> implicit-GEMM kernel.  Returns ``(y, stats_filled)``: when ``stats`` (fp32 [2*Cout]
     accumulator) is given and the kernel that ran supports it, its epilogue has added the output's
@@ -236,13 +258,13 @@ def conv2d(x, conv: torch.nn.Conv2d, box=None, stats=None):
     if _is_gemm_conv(x, conv):
         N, C, H, W = x.shape
         x2 = x.permute(0, 2, 3, 1).reshape(N * H * W, C)             # view: NHWC rows
-        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C), owner=w, box=box, stats=stats)     # [M, Cout]
+        y2 = _gemm.linear(x2, w.reshape(w.shape[0], C), owner=w, box=box, stats=stats, park=park)     # [M, Cout]
         return y2.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2), stats is not None   # logical NCHW, NHWC memory
     if _is_stem_conv(x, conv):
         return _StemConvFn.apply(x, w, stats), stats is not None
     from . import conv as _conv
     if conv.bias is None and _conv.supported(x, w, conv.stride, conv.padding, conv.dilation, conv.groups):
-        return _conv.conv2d(x, w, conv.stride[0], conv.padding[0], stats), stats is not None
+        return _conv.conv2d(x, w, conv.stride[0], conv.padding[0], stats, park), stats is not None
     return F.conv2d(x, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups), False
 
 
@@ -255,16 +277,18 @@ def _stats_buffer(bn, C: int, device):
     return buf
 
 
-def conv_bn_act(x, conv, bn, relu: bool, residual=None, skip_box=None, input_box=None):
+def conv_bn_act(x, conv, bn, relu: bool, residual=None, skip_box=None, input_box=None, park_box=None):
     """``input_box``: this conv consumes the block input whose skip gradient will arrive through the
-    box; ``skip_box``: this BN's residual IS that block input (grad_sink.GradBox)."""
+    box; ``skip_box``: this BN's residual IS that block input, or (projection block) this BN is the
+    downsample BN / the block's last BN exchanging the ReLU sign bits; ``park_box``: this conv's input
+    gradient is handed to the box's consumer instead of being returned (grad_sink.GradBox)."""
     C = conv.out_channels
     fused_bn = _lib is not None and bn.weight is not None and bool(_lib.b200dp_bn_supported(C)) and \
         (residual is None or residual.dtype == torch.bfloat16)
     # batch statistics come out of the conv / GEMM epilogue (no separate pass over y)
     want_stats = _FUSE_STATS and fused_bn and bn.training and C <= 2048 and x.dtype == torch.bfloat16
     stats = _stats_buffer(bn, C, x.device) if want_stats else None
-    y, filled = conv2d(x, conv, box=input_box, stats=stats)
+    y, filled = conv2d(x, conv, box=input_box, stats=stats, park=park_box)
     if stats is not None and not filled:
         stats = None
     if fused_bn and bn_supported(y, C):
@@ -306,6 +330,36 @@ class _MaxPoolFn(torch.autograd.Function):
                                     torch.cuda.current_stream(dy.device).cuda_stream))
         counters.bump("maxpool_bwd")
         return dx
+
+
+class _GlobalAvgPoolFn(torch.autograd.Function):
+    """mean over H, W of an NHWC bf16 activation -> [N, C]; the backward is one broadcast write."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, C, H, W = x.shape
+        y = torch.empty((N, C), dtype=x.dtype, device=x.device)
+        _ck(_lib.b200dp_avgpool_fwd(x.data_ptr(), y.data_ptr(), N, H * W, C,
+                                    torch.cuda.current_stream(x.device).cuda_stream))
+        counters.bump("avgpool_fwd")
+        ctx.shape = (N, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, C, H, W = ctx.shape
+        dy = dy.contiguous()
+        dx = torch.empty((N, C, H, W), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        _ck(_lib.b200dp_avgpool_bwd(dy.data_ptr(), dx.data_ptr(), N, H * W, C,
+                                    torch.cuda.current_stream(dy.device).cuda_stream))
+        counters.bump("avgpool_bwd")
+        return dx
+
+
+def global_avg_pool(x):
+    if _nhwc_ok(x) and x.shape[1] % 8 == 0 and hasattr(_lib, "b200dp_avgpool_fwd"):
+        return _GlobalAvgPoolFn.apply(x)
+    return x.mean(dim=(2, 3))
 
 
 def max_pool_3x3_s2(x):

@@ -37,12 +37,13 @@ def conv_bn_act_reference(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool,
 
 
 def conv_bn_act(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, relu: bool = True,
-                residual: Optional[torch.Tensor] = None, skip_box=None, input_box=None):
+                residual: Optional[torch.Tensor] = None, skip_box=None, input_box=None, park_box=None):
     """``skip_box`` / ``input_box`` (kernel path only): see ``ops.grad_sink.GradBox`` — the block's last
     BN parks the skip-connection gradient, the block's first conv adds it in its dgrad epilogue."""
     k = _kernels(x)
     if k is not None and k.has("conv_bn_act"):
-        return k.conv_bn_act(x, conv, bn, relu, residual, skip_box=skip_box, input_box=input_box)
+        return k.conv_bn_act(x, conv, bn, relu, residual, skip_box=skip_box, input_box=input_box,
+                             park_box=park_box)
     return conv_bn_act_reference(x, conv, bn, relu, residual)
 
 
@@ -62,6 +63,9 @@ def max_pool_3x3_s2(x):
 
 
 def global_avg_pool(x):
+    k = _kernels(x)
+    if k is not None and k.has("global_avg_pool"):
+        return k.global_avg_pool(x)
     return x.mean(dim=(2, 3))
 
 

@@ -31,7 +31,7 @@ def register(lib, have):
     _lib = lib
     vp, i, f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.b200dp_gemm_bf16.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp, i, i, f, i,
-                                     i, i, i, vp, ctypes.c_uint64]
+                                     i, i, i, vp, vp, ctypes.c_uint64]
     lib.b200dp_gemm_bf16.restype = i
     lib.b200dp_gemm_last_error.restype = ctypes.c_char_p
     if hasattr(lib, "b200dp_cast_acc_zero"):
@@ -44,7 +44,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
          a_mn: bool = False, b_mn: bool = False, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, preact: Optional[torch.Tensor] = None,
          act: int = 0, out_mode: int = 0, alpha: float = 1.0, splits: int = 1, block_n: int = 0,
-         max_ctas: int = 0, two_cta: Optional[bool] = None, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+         max_ctas: int = 0, two_cta: Optional[bool] = None, stats: Optional[torch.Tensor] = None,
+         res_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Raw kernel call.  ``a``: [M,K] (K-major) or [K,M] (MN-major) bf16 with contiguous rows;
     ``b``: [N,K] or [K,N]; ``out``: [M,N] bf16 (out_mode 0) or fp32 (1: atomic add, 2: store)."""
     assert _lib is not None, "libb200dp_kernels.so not loaded"
@@ -59,6 +60,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, M: int, N: int, K:
         preact.data_ptr() if preact is not None else None,
         act, out_mode, float(alpha), splits, block_n, max_ctas, int(_want_2cta(M, N, K, two_cta)),
         stats.data_ptr() if stats is not None else None,
+        res_mask.data_ptr() if res_mask is not None else None,
         torch.cuda.current_stream(a.device).cuda_stream)
     if rc != 0:
         raise RuntimeError("b200dp_gemm_bf16: " + (_lib.b200dp_gemm_last_error() or b"").decode())
@@ -169,10 +171,11 @@ def bias_grad(dz: torch.Tensor, N: int, M: int, dtype) -> torch.Tensor:
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, act, residual, owner=None, box=None, stats=None):
+    def forward(ctx, x, weight, bias, act, residual, owner=None, box=None, stats=None, park=None):
         K = weight.shape[1]
         ctx.owner = owner if owner is not None else weight
         ctx.box = box if (box is not None and ctx.needs_input_grad[0]) else None
+        ctx.park = park if ctx.needs_input_grad[0] else None
         if ctx.box is not None:
             ctx.box.armed = True
         if ctx.needs_input_grad[1]:
@@ -213,23 +216,29 @@ class _LinearFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
-            skip = None
-            if ctx.box is not None and ctx.box.dres is not None:
-                skip = ctx.box.dres                 # skip-connection gradient of the same block input
-                ctx.box.dres = None
+            skip = skip_mask = None
+            if ctx.box is not None:
+                skip, skip_mask = ctx.box.take()    # skip-connection gradient of the same block input
+            if skip is not None:
                 if skip.dim() == 4:                 # NHWC activation -> its [M, C] matrix (a view)
                     skip = skip.permute(0, 2, 3, 1).reshape(M, K)
                 else:
                     skip = skip.reshape(M, K)
                 if not skip.is_contiguous():
                     skip = skip.contiguous()
-            gemm(dz, weight, dx, M, K, N, b_mn=True, residual=skip)        # dx = dz @ W (+ skip gradient)
+                if skip_mask is not None and (K % 64):      # kernel limit: apply the sign bits here
+                    bits = (skip_mask.view(M, K // 8, 1) >> torch.arange(8, device=skip.device, dtype=torch.uint8)) & 1
+                    skip = skip * bits.view(M, K).to(skip.dtype)
+                    skip_mask = None
+            gemm(dz, weight, dx, M, K, N, b_mn=True, residual=skip, res_mask=skip_mask)   # dx = dz @ W (+ skip)
             dx = dx.view(ctx.x_shape)
+            if ctx.park is not None and ctx.park.park(dx):
+                dx = None                           # the block's first conv adds it in its dgrad epilogue
         if ctx.needs_input_grad[1]:
             dw = wgrad(dz, x2, N, K, M, weight.dtype, owner=ctx.owner)     # dW = dz^T @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = bias_grad(dz, N, M, ctx.bias_dtype)
-        return dx, dw, db, None, dres, None, None, None
+        return dx, dw, db, None, dres, None, None, None, None
 
 
 def act_backward(dy2: torch.Tensor, z: torch.Tensor, act: int) -> torch.Tensor:
@@ -358,9 +367,10 @@ def qkv_proj(x, weight, bias):
     return _QKVFn.apply(x, weight, bias)
 
 
-def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, owner=None, box=None, stats=None):
+def linear(x, weight, bias=None, act: Optional[str] = None, residual=None, owner=None, box=None, stats=None,
+           park=None):
     """``owner``: the parameter whose storage ``weight`` is a 2D view of (a 1x1 conv weight), so the
     weight gradient can be written into its gradient-bucket slot directly.  ``box``: a
     ``grad_sink.GradBox`` through which a later node hands this layer the skip-connection gradient of
     the same input (added in the dgrad epilogue)."""
-    return _LinearFn.apply(x, weight, bias, ACT[act], residual, owner, box, stats)
+    return _LinearFn.apply(x, weight, bias, ACT[act], residual, owner, box, stats, park)

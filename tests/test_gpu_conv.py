@@ -161,39 +161,76 @@ def test_grad_sink_matches_autograd_path():
         assert _rel(a2[n], 2 * a1[n]) < 2e-2, n
 
 
-def test_bottleneck_skip_gradient_goes_through_dgrad_epilogue():
-    """Identity bottleneck: the skip-connection gradient is added by conv1's dgrad GEMM epilogue
-    (ops.grad_sink.GradBox).  Oracle: the same kernels with the box disabled (autograd's stand-alone add),
-    plus a loose check against the fp32 reference composition."""
+@pytest.mark.parametrize("kind", ["identity", "projection_s1", "projection_s2"])
+def test_bottleneck_skip_gradient_goes_through_dgrad_epilogue(kind):
+    """The block input feeds conv1 and the skip branch; its second gradient is added by conv1's dgrad GEMM
+    epilogue (ops.grad_sink.GradBox) — identity block: bn3's unmasked dy + ReLU sign bits; projection block:
+    the downsample conv's dgrad, with the sign bits handed to the downsample BN.  Oracle: the same kernels
+    with the boxes disabled (autograd's stand-alone add, masked copy written by the BN backward), plus a
+    loose check against the fp32 reference composition."""
     import copy
+    import torch.nn as nn
     from distributed_torch_horovod_gcp_b200.models.resnet import Bottleneck
-    from distributed_torch_horovod_gcp_b200.ops import functional as F2, counters
+    from distributed_torch_horovod_gcp_b200.ops import functional as F2
     _kern()
     torch.manual_seed(4)
-    blk = Bottleneck(256, 64).cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
+    if kind == "identity":
+        blk, cin, hw = Bottleneck(256, 64), 256, 14
+    else:
+        stride = 1 if kind == "projection_s1" else 2
+        ds = nn.Sequential(nn.Conv2d(128, 256, 1, stride, bias=False), nn.BatchNorm2d(256))
+        blk, cin, hw = Bottleneck(128, 64, stride, ds), 128, 28
+    blk = blk.cuda().to(torch.bfloat16).to(memory_format=torch.channels_last)
     ref = copy.deepcopy(blk).float()
-    x = torch.randn(8, 256, 14, 14, device="cuda").to(torch.bfloat16).contiguous(
-        memory_format=torch.channels_last).requires_grad_(True)
-    g = torch.randn(8, 256, 14, 14, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-    grads = []
+    x0 = torch.randn(8, cin, hw, hw, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        oshape = blk(x0).shape
+    g = torch.randn(oshape, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    grads, wgrads = [], []
     real_box = F2.new_grad_box
     for use_box in (True, False, True):
         F2.new_grad_box = real_box if use_box else (lambda t: None)
         try:
-            x.grad = None
+            # x is an intermediate (as in the network), so that a withheld gradient would go missing
+            leaf = x0.clone().requires_grad_(True)
+            x = leaf * 1.0
+            blk.zero_grad()
             blk(x).backward(g)
-            grads.append(x.grad.float().clone())
+            grads.append(leaf.grad.float().clone())
+            wgrads.append(blk.conv1.weight.grad.float().clone())
         finally:
             F2.new_grad_box = real_box
     assert _rel(grads[0], grads[1]) < 1e-2          # fused add == stand-alone add
     assert _rel(grads[2], grads[1]) < 1e-2          # the box is per-forward state: second use is clean
-    xr = x.detach().float().requires_grad_(True)
+    assert _rel(wgrads[0], wgrads[1]) < 1e-2
+    xr = x0.detach().float().requires_grad_(True)
     F2._FORCE_REFERENCE = True
     try:
         ref(xr).backward(g.float())
     finally:
         F2._FORCE_REFERENCE = False
     assert _rel(grads[0], xr.grad) < 1e-1           # bf16 activations / BN statistics vs fp32 end to end
+
+
+def test_gemm_masked_residual():
+    """dgrad GEMM with a bit-masked residual (C = A B + mask(R)): the skip gradient of an identity block
+    is bn3's incoming gradient with the block's ReLU sign bits (1 byte / 8 channels) applied in the epilogue."""
+    from distributed_torch_horovod_gcp_b200.ops import gemm as G
+    _kern()
+    torch.manual_seed(9)
+    M, N, K = 1000, 256, 64
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    b = (torch.randn(N, K, device="cuda") * 0.1).to(torch.bfloat16)
+    r = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+    keep = torch.rand(M, N, device="cuda") > 0.5
+    bits = (keep.view(M, N // 8, 8).to(torch.uint8) << torch.arange(8, device="cuda", dtype=torch.uint8)).sum(
+        dim=2).to(torch.uint8).contiguous()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    G.gemm(a, b, out, M, N, K, residual=r, res_mask=bits)
+    ref = a.float() @ b.float().t() + r.float() * keep.float()
+    assert _rel(out.float(), ref) < 1e-2
+    G.gemm(a, b, out, M, N, K, residual=r)
+    assert _rel(out.float(), a.float() @ b.float().t() + r.float()) < 1e-2
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,hw", [(64, 256, 1, 1, 28), (64, 64, 3, 1, 28), (128, 256, 3, 1, 14),
