@@ -196,7 +196,6 @@ class SymmRuntime:
         # staging for tensors that do not live in symmetric memory
         self.stage_bytes = int(os.environ.get("B200DP_STAGING_BYTES", str(64 << 20)))
         self.stage = self.alloc(self.stage_bytes)
-        self.scratch = torch.empty(self.stage_bytes, dtype=torch.uint8, device=self.device)
         self.max_blocks = int(os.environ.get("B200DP_COMM_BLOCKS", "0"))
         self.algo_override = os.environ.get("B200DP_ALGO", "auto").lower()
         self.launches = 0

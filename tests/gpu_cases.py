@@ -465,7 +465,7 @@ def allreduce_large(hvd):
     from distributed_torch_horovod_gcp_b200.runtime import symm as S
     r, n = hvd.rank(), hvd.size()
     dev = s.device
-    for numel in ((64 << 20) + 4, (256 << 20)):
+    for numel in ((64 << 20) + 4, (256 << 20) + 4):
         t = hvd.symm_empty(numel, torch.float32)
         torch.manual_seed(r)
         base = torch.randn(1 << 20, device=dev)
