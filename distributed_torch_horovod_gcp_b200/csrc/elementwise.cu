@@ -518,6 +518,73 @@ __global__ void __launch_bounds__(THREADS) maxpool_bwd_kernel(const uint4* __res
   }
 }
 
+
+// Backward, H and W even (the network case): one thread owns a 2x2 input patch x 8 channels.  The patch is
+// covered by exactly the four windows (a..a+1, b..b+1), so dy / arg-max are loaded once per window (96 B in
+// for 64 B out instead of 2.25 windows per pixel), the byte arg-max comparison is done 4 channels at a time
+// (SWAR equality -> PRMT sign-replicate -> 16-bit lane masks) and contributions are summed with packed bf16
+// adds (ATen's NHWC backward also accumulates in bf16).
+__device__ __forceinline__ uint32_t prmt_msb(uint32_t a, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+  return d;
+}
+template <int TAP>
+__device__ __forceinline__ void pool_take(uint4& acc, const uint4& d, const uint2& ix) {
+  constexpr uint32_t t4 = (uint32_t)TAP * 0x01010101u;
+  // byte == TAP  <=>  MSB of ((byte ^ TAP) | 0x80) - 1 is clear   (arg-max bytes are 0..8)
+  const uint32_t e0 = ~(((ix.x ^ t4) | 0x80808080u) - 0x01010101u);
+  const uint32_t e1 = ~(((ix.y ^ t4) | 0x80808080u) - 0x01010101u);
+  const uint32_t m0 = d.x & prmt_msb(e0, 0x9988u), m1 = d.y & prmt_msb(e0, 0xbbaau);
+  const uint32_t m2 = d.z & prmt_msb(e1, 0x9988u), m3 = d.w & prmt_msb(e1, 0xbbaau);
+  asm("add.rn.bf16x2 %0, %0, %1;" : "+r"(acc.x) : "r"(m0));
+  asm("add.rn.bf16x2 %0, %0, %1;" : "+r"(acc.y) : "r"(m1));
+  asm("add.rn.bf16x2 %0, %0, %1;" : "+r"(acc.z) : "r"(m2));
+  asm("add.rn.bf16x2 %0, %0, %1;" : "+r"(acc.w) : "r"(m3));
+}
+__global__ void __launch_bounds__(THREADS) maxpool_bwd_patch_kernel(const uint4* __restrict__ dy,
+                                                                    const uint2* __restrict__ idx, uint4* dx,
+                                                                    int N, int H, int W, int OH, int OW, int V) {
+  const int HP = H / 2, WP = W / 2;
+  const long long total = (long long)N * HP * WP * V;
+  for (long long i = (long long)blockIdx.x * THREADS + threadIdx.x; i < total;
+       i += (long long)gridDim.x * THREADS) {
+    const int cv = (int)(i % V);
+    long long t = i / V;
+    const int b = (int)(t % WP); t /= WP;
+    const int a = (int)(t % HP);
+    const int n = (int)(t / HP);
+    uint4 p00 = make_uint4(0, 0, 0, 0), p01 = p00, p10 = p00, p11 = p00;   // (row 2a+i, col 2b+j)
+    const long long o00 = (((long long)n * OH + a) * OW + b) * V + cv;
+    const bool hb = b + 1 < OW, ha = a + 1 < OH;
+    {   // window (a, b): rows 2a-1..2a+1, cols 2b-1..2b+1 -> taps (1,1) (1,2) (2,1) (2,2)
+      const uint4 d = dy[o00];
+      const uint2 ix = idx[o00];
+      pool_take<4>(p00, d, ix); pool_take<5>(p01, d, ix); pool_take<7>(p10, d, ix); pool_take<8>(p11, d, ix);
+    }
+    if (hb) {   // window (a, b+1): cols 2b+1..2b+3 -> taps (1,0) (2,0)
+      const uint4 d = dy[o00 + V];
+      const uint2 ix = idx[o00 + V];
+      pool_take<3>(p01, d, ix); pool_take<6>(p11, d, ix);
+    }
+    if (ha) {   // window (a+1, b): rows 2a+1..2a+3 -> taps (0,1) (0,2)
+      const uint4 d = dy[o00 + (long long)OW * V];
+      const uint2 ix = idx[o00 + (long long)OW * V];
+      pool_take<1>(p10, d, ix); pool_take<2>(p11, d, ix);
+      if (hb) {   // window (a+1, b+1) -> tap (0,0)
+        const uint4 d2 = dy[o00 + (long long)OW * V + V];
+        const uint2 ix2 = idx[o00 + (long long)OW * V + V];
+        pool_take<0>(p11, d2, ix2);
+      }
+    }
+    const long long x00 = (((long long)n * H + 2 * a) * W + 2 * b) * V + cv;
+    dx[x00] = p00;
+    dx[x00 + V] = p01;
+    dx[x00 + (long long)W * V] = p10;
+    dx[x00 + (long long)W * V + V] = p11;
+  }
+}
+
 // ---- stem im2col: 7x7 / stride 2 / pad 3 over NHWC bf16 with C = 3 ------------------------------------
 // Turns the ResNet stem into a plain GEMM for the tcgen05 kernel: A[m][k], m = (n, oh, ow),
 // k = kh*24 + j, j = kw*3 + c for j < 21 and three more elements (the next pixel) for j = 21..23 that
@@ -840,6 +907,16 @@ int b200dp_maxpool_bwd(const void* dy, const void* idx, void* dx, int N, int H, 
                        unsigned long long stream) {
   if (C % 8) return -1;
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1, V = C / 8;
+  if (H % 2 == 0 && W % 2 == 0) {
+    const long long patches = (long long)N * (H / 2) * (W / 2) * V;
+    int pgrid = (int)((patches + THREADS - 1) / THREADS);
+    if (pgrid > 148 * 16) pgrid = 148 * 16;
+    maxpool_bwd_patch_kernel<<<pgrid, THREADS, 0, (cudaStream_t)(uintptr_t)stream>>>(
+        (const uint4*)dy, (const uint2*)idx, (uint4*)dx, N, H, W, OH, OW, V);
+    cudaError_t pe = cudaGetLastError();
+    if (pe != cudaSuccess) return fail("maxpool_bwd launch", pe);
+    return 0;
+  }
   const long long total = (long long)N * H * W * V;
   int grid = (int)((total + THREADS - 1) / THREADS);
   if (grid > 148 * 16) grid = 148 * 16;

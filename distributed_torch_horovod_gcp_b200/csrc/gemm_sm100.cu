@@ -312,6 +312,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
+  __syncthreads();                    // (CTA-scope barrier for the tcgen05.alloc result: racecheck does not model
+                                      //  barrier.cluster as ordering the allocator's shared-memory write)
   cluster_sync_all();                 // both CTAs' barriers are initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
