@@ -39,6 +39,8 @@ def register(lib, have):
     lib.b200dp_conv_wgrad.argtypes = [vp, vp, vp] + [i] * 12 + [u64]
     lib.b200dp_conv_last_error.restype = ctypes.c_char_p
     lib.b200dp_cast_acc_zero.argtypes = [vp, vp, ll, i, i, i, u64]
+    if hasattr(lib, "b200dp_multi_cast_acc_zero"):
+        lib.b200dp_multi_cast_acc_zero.argtypes = [vp, i, u64]
     have["conv3x3"] = True
     have["conv_implicit_gemm"] = True
 
@@ -125,11 +127,14 @@ def conv_wgrad(dy, x, weight, stride: int, pad: int) -> Optional[torch.Tensor]:
     if dst is None:
         dst = torch.empty_like(weight, memory_format=torch.channels_last)
         acc, ret = False, dst
-    rc = _lib.b200dp_cast_acc_zero(ws.data_ptr(), dst.data_ptr(), weight.numel(),
-                                   int(dst.dtype == torch.bfloat16), int(acc), 1, st)
-    if rc != 0:
-        raise RuntimeError("cast_acc_zero failed")
-    counters.bump("conv_wgrad", 2)
+    if done is not None and grad_sink.defer_cast(_lib, ws, dst, weight.numel(), acc):
+        counters.bump("conv_wgrad", 1)       # converted with the bucket's other gradients (multi-tensor pass)
+    else:
+        rc = _lib.b200dp_cast_acc_zero(ws.data_ptr(), dst.data_ptr(), weight.numel(),
+                                       int(dst.dtype == torch.bfloat16), int(acc), 1, st)
+        if rc != 0:
+            raise RuntimeError("cast_acc_zero failed")
+        counters.bump("conv_wgrad", 2)
     if done is not None:
         done()
     return ret

@@ -36,6 +36,8 @@ def register(lib, have):
     lib.b200dp_gemm_last_error.restype = ctypes.c_char_p
     if hasattr(lib, "b200dp_cast_acc_zero"):
         lib.b200dp_cast_acc_zero.argtypes = [vp, vp, ctypes.c_longlong, i, i, i, ctypes.c_uint64]
+    if hasattr(lib, "b200dp_multi_cast_acc_zero"):
+        lib.b200dp_multi_cast_acc_zero.argtypes = [vp, i, ctypes.c_uint64]
     have["gemm"] = True
     have["linear"] = True
 
@@ -148,12 +150,13 @@ def wgrad(dz: torch.Tensor, x2: torch.Tensor, N: int, K: int, M: int, dtype, own
             ws = _workspace(key, N * K, dz.device).view(N, K)
             gemm(dz, x2, ws, N, K, M, a_mn=True, b_mn=True, out_mode=1, splits=splits)
             dw = out if out is not None else torch.empty((N, K), dtype=dtype, device=dz.device)
-            rc = _lib.b200dp_cast_acc_zero(ws.data_ptr(), dw.data_ptr(), N * K, int(dtype == torch.bfloat16),
-                                           int(acc and out is not None), 1,
-                                           torch.cuda.current_stream(dz.device).cuda_stream)
-            if rc != 0:
-                raise RuntimeError("cast_acc_zero failed")
-            counters.bump("cast_acc_zero")
+            if not (done is not None and out is not None and grad_sink.defer_cast(_lib, ws, dw, N * K, acc)):
+                rc = _lib.b200dp_cast_acc_zero(ws.data_ptr(), dw.data_ptr(), N * K, int(dtype == torch.bfloat16),
+                                               int(acc and out is not None), 1,
+                                               torch.cuda.current_stream(dz.device).cuda_stream)
+                if rc != 0:
+                    raise RuntimeError("cast_acc_zero failed")
+                counters.bump("cast_acc_zero")
     if done is not None:
         done()
         return None
