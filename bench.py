@@ -332,8 +332,10 @@ def selfcheck(wl, hvd, world, rank):
     digests = hvd.allgather_object(h.hexdigest())
     opt.remove_hooks()
     return {"max_rel_err": worst, "replicas_bit_identical": len(set(digests)) == 1,
-            "expected": ("<= 2^-8 (one bf16 ulp: torch updates bf16 parameters in bf16, the fused engine "
-                         "rounds fp32 masters once)" if wl.dtype_name == "bf16" else "fp32 rounding (~1e-6)"),
+            "expected": ("a few bf16 ulps (2^-8 = 0.0039 each): the NCCL arm rounds the reduced gradient to bf16 "
+                         "and torch updates bf16 parameters in bf16; the fused engine sums in fp32 (another "
+                         "order) and rounds the fp32 master once — measured 0.008-0.009 at 2 and 8 GPUs"
+                         if wl.dtype_name == "bf16" else "fp32 rounding (~1e-6)"),
             "what": "fused NVLink allreduce+update vs NCCL all_reduce + torch optimizer on identical "
                     "local gradients; per-tensor max|a-b| / max|b|, worst tensor"}
 

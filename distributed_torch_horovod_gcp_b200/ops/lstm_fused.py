@@ -88,6 +88,9 @@ def available(model, x: torch.Tensor) -> bool:
             + model.linear3.out_features <= 12000)
 
 
+_warned_cudnn = False
+
+
 def forward(model, x, hidden):
     """Persistent recurrence kernel (K5, ops/lstm_rec.py; cuDNN only for shapes it does not cover)
     + fused head (K6)."""
@@ -97,6 +100,14 @@ def forward(model, x, hidden):
         seq, model.hidden = lstm_rec.lstm_recurrent(x, hidden[0], hidden[1], lstm.weight_ih_l0,
                                                     lstm.weight_hh_l0, lstm.bias_ih_l0, lstm.bias_hh_l0)
     else:
+        global _warned_cudnn
+        if not _warned_cudnn:
+            _warned_cudnn = True
+            import logging
+            logging.getLogger("b200dp").warning(
+                "LSTM shape (layers=%d, hidden=%d, features=%d, bidirectional=%s) is outside the persistent "
+                "recurrence kernel (1 layer, H=256, F<=32): using the cuDNN RNN for this module",
+                model.n_layers, model.h_size, model.n_features, model.directions == 2)
         seq, model.hidden = lstm(x, hidden)
     if not seq.is_contiguous():
         seq = seq.contiguous()
