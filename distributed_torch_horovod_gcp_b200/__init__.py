@@ -8,7 +8,8 @@ for 8xB200 over NVLink 5 / NVSwitch:
   (``init/rank/size/local_rank/DistributedOptimizer/broadcast_parameters/allreduce``…)
 * ``.runtime``   — C++ symmetric-memory runtime (cuMem VMM + multicast, fd exchange)
 * ``.ops``       — hand-written sm_100a kernels (fused allreduce+optimizer, tcgen05 GEMM,
-  conv, batch-norm, LSTM) and their autograd wrappers
+  implicit-GEMM convolution, flash attention, persistent LSTM recurrence, batch-norm / layer-norm /
+  pooling) and their autograd wrappers
 * ``.parallel``  — bucket planner, backward hooks, side-stream overlap
 * ``.models``    — LSTM (reference model), ResNet-18/50/152, ViT-B/16
 * ``.launch``    — ``horovodrun``-shaped launcher (``-np N -H host:slots``)
@@ -19,6 +20,6 @@ Usage mirrors Horovod::
     hvd.init()
 """
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 from . import _state  # noqa: F401  (process-wide runtime state)
